@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""Benchmark of the OTPose temporal fusion head on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one pass of the whole hot path over one
+batch of synthetic person-clips: rough heat maps (5B,17,96,72) + margin -> fusion
+prologue -> 3 ConvTransformer encoders -> pyramid 1x1 convs -> RSB chains ->
+5 x (offset conv, mask conv, modulated DCN) -> refined heat maps -> get_final_preds.
+One JSON line on stdout (rank 0).  N > 1 is launched by torchrun: one process per
+GPU, clips sharded by rank (weak scaling, no data-path collective; NCCL is only
+the barrier / max-over-ranks plumbing).
+
+`--impl reference` times the reference's own CPU implementation of the path --
+the oracle port (reference ConvTransformer/RSB semantics in torch CPU fp32 +
+torchvision deform_conv2d + NumPy get_final_preds) -- on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, J = 96, 72, 17
+C8 = 8 * J
+T = H * W
+METRIC = "temporal_head_person_clips_per_s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="person-clips per GPU per step")
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--cpu-clips", type=int, default=2, help="clips per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def shard_seed(base: int, rank: int) -> int:
+    """Every rank draws different synthetic clips (independent shards of the batch)."""
+    return base + 1000 * rank
+
+
+def dist_max(value: float, device=None) -> float:
+    """Max over ranks of a python float (device tensor for NCCL, CPU for gloo)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device if dist.get_backend() == "nccl" else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+# ----------------------------------------------------------------------------------------
+# algorithmic work per step (formulas stated in DESIGN.md)
+# ----------------------------------------------------------------------------------------
+def block_tokens(t):
+    """(C, T') of every TransformerBlock launch of one head forward."""
+    t1, t2 = t // 2, t // 4
+    enc = [(C8, t)] * 6 + [(C8, t1), (C8, t2)]
+    return enc + enc + [(J, t)] * 6
+
+
+def algorithmic_work(b, t=T):
+    """kernel name -> (bound, work per step): FLOPs (2*MAC) for tensor-bound kernels,
+    bytes for HBM-bound ones."""
+    blocks = block_tokens(t)
+    big = [(c, tt) for c, tt in blocks if c == C8]
+    w = {}
+    flops = lambda f, bl: float(sum(f(c, tt) for c, tt in bl)) * b   # noqa: E731
+    w["block_front"] = ("tensor", flops(lambda c, tt: (4 * c * c + 2 * c * (c // (2 if c == C8 else 1))) * tt, blocks))
+    w["block_apply"] = ("tensor", flops(lambda c, tt: 2 * c * c * tt, blocks))
+    w["block_back"] = ("tensor", flops(lambda c, tt: 18 * c * c * tt, blocks))
+    w["tc_block_front"] = ("tensor", flops(lambda c, tt: (4 * c * c + 2 * c * (c // 2)) * tt, big))
+    w["tc_block_apply"] = ("tensor", flops(lambda c, tt: 2 * c * c * tt, big))
+    w["tc_block_back"] = ("tensor", flops(lambda c, tt: 18 * c * c * tt, big))
+    # conv2d launches: 2 RSB chains + 5 x (offset, mask) convs  
+    w["conv2d"] = ("tensor", (0.116e9 + 0.868e9 + 5 * (1.218e9 + 0.609e9)) * t / T * b)
+    w["tc_offset_mask_conv"] = ("tensor", 5 * (1.218e9 + 0.609e9) * t / T * b)
+    # HBM-bound: read offsets+masks (459 ch) + x (17) + write/accumulate out (17), fp32, x5 dilations
+    w["mdcn_fwd"] = ("hbm", 5.0 * (459 + 17 + 17) * t * 4 * b)
+    w["final_preds"] = ("hbm", float(J * t * 4 + J * 28) * b)
+    w["fusion_sum"] = ("hbm", float((5 * J + J + 1) * t * 4) * b)
+    w["fusion_stack"] = ("hbm", float((5 * J + J + 1 + 2 * C8 + 2 * J) * t * 4) * b)
+    w["pyramid_conv1x1"] = ("hbm", 2.0 * (C8 * (t + t // 2 + t // 4) + J * t) * 4 * b)
+    return w
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm": p["hbm_gbs"], "tensor": p["bf16_tflops_sustained"], "source": "measured"}
+    except Exception:
+        return {"hbm": 6650.0, "tensor": 1400.0, "source": "fallback"}
+
+
+# ----------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ----------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for ts, r in self.rows if t0 <= ts <= t1 and len(r) >= 7] or \
+               [r for _, r in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return float("nan")
+        return {"sm_mhz": statistics.median(num(r[0]) for r in rows), "sm_max_mhz": num(rows[0][1]),
+                "power_w_max": max(num(r[2]) for r in rows), "samples": len(rows), "reasons": reasons}
+
+
+# ----------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline (the ONLY place bench.py touches oracle/)
+# ----------------------------------------------------------------------------------------
+def cpu_reference(clips, steps, warmup):
+    import torch
+    from oracle import head_oracle as ho
+    from otpose_b200.model import OTPose, default_cfg
+    from otpose_b200.utils import synthetic as syn
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    shapes = {k: v.shape for k, v in OTPose(default_cfg((H, W))).state_dict().items()}
+    sd = syn.fill_state_dict(shapes, seed=2024)
+    rough, margin = syn.synth_rough_heatmaps(clips, J, H, W), syn.synth_margin(clips)
+    center, scale = syn.synth_center_scale(clips)
+
+    def step():
+        with torch.no_grad():
+            out = ho.head_forward(sd, rough, margin)[0]
+        ho.get_final_preds(out.numpy(), center, scale)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return {"value": clips * steps / dt, "unit": "clips/s", "cores": threads, "kind": "port",
+            "sample": f"{steps} steps x {clips} clips of the bench workload (96x72, 17 joints), torch CPU fp32 "
+                      f"oracle port, {threads} threads", "ms_per_step": 1e3 * dt / steps}
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    cb = cpu_reference(args.cpu_clips, max(1, min(args.steps, 5)), min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "clips/s", "n_gpus": args.gpus,
+            "steps": max(1, min(args.steps, 5)), "warmup": min(args.warmup, 1), "ms_per_step": cb["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args.cpu_clips, "fp32"),
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(batch, precision):
+    return {"workload": f"OTPose temporal head fwd (fusion prologue + flow/temporal ConvTransformer encoders + "
+                        f"RSB + 5x offset/mask conv + modulated DCN + get_final_preds), {batch} person-clips/GPU, "
+                        f"5 frames, {H}x{W} heat maps, {J} joints (BASELINE configs[1] batch; HRNet backbone out of scope)",
+            "clips_per_gpu": batch, "heatmap": [H, W], "joints": J, "precision": precision,
+            "l2": "per-step working set (activations > 1 GB at 32 clips) far exceeds the 126 MB L2; no explicit flush"}
+
+
+# ----------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from otpose_b200 import _lib
+    from otpose_b200.model import OTPose, default_cfg
+    from otpose_b200.utils import heatmap, synthetic as syn
+
+    rank, local_rank, world = dist_env()
+    lib = _lib.load()           # raises when the CUDA library is missing -- no fallback path exists
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    precision = args.precision
+    if precision == "auto":
+        precision = "bf16" if lib.otp_has_tensor_core_path() else "fp32"
+    b = args.batch
+
+    model = OTPose(default_cfg((H, W)), precision=precision)
+    model.load_state_dict(syn.fill_state_dict({k: v.shape for k, v in model.state_dict().items()}, seed=2024))
+    model = model.to(dev).eval()
+    rough_host = syn.synth_rough_heatmaps(b, J, H, W, seed=shard_seed(1234, rank)).pin_memory()
+    margin_host = syn.synth_margin(b, seed=shard_seed(1236, rank)).pin_memory()
+    center, scale = (torch.from_numpy(a).to(dev) for a in syn.synth_center_scale(b, seed=shard_seed(1237, rank)))
+    rough, margin = rough_host.to(dev), margin_host.to(dev)
+    rough_stage = torch.empty_like(rough)
+    margin_stage = torch.empty_like(margin)
+    preds_host = torch.empty((b, J, 2), dtype=torch.float32).pin_memory()
+    vals_host = torch.empty((b, J, 1), dtype=torch.float32).pin_memory()
+
+    def step_resident():
+        out = model.forward_head(rough, margin)[0]
+        return heatmap.final_preds_cuda(out, center, scale)
+
+    def step_e2e():
+        rough_stage.copy_(rough_host, non_blocking=True)
+        margin_stage.copy_(margin_host, non_blocking=True)
+        out = model.forward_head(rough_stage, margin_stage)[0]
+        r = heatmap.final_preds_cuda(out, center, scale)
+        preds_host.copy_(r["preds"], non_blocking=True)
+        vals_host.copy_(r["maxvals"], non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def timed(fn, steps):
+        barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        barrier()
+        return dist_max(e0.elapsed_time(e1), dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    wall0 = time.time()
+    launches0 = lib.otp_launch_count()
+    lib.otp_profile_enable(1)
+    ms = timed(step_resident, args.steps)
+    prof = _lib.profile_read()
+    lib.otp_profile_enable(0)
+    launches = lib.otp_launch_count() - launches0
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    wall1 = time.time()
+    clocks = sampler.stop(wall0, wall1) if sampler else None
+
+    if rank == 0:
+        peaks = load_peaks()
+        work = algorithmic_work(b)
+        kernels = {}
+        for name, (tot_ms, cnt) in prof.items():
+            per_step = tot_ms / args.steps
+            k = {"ms_per_step": round(per_step, 4), "launches_per_step": cnt / args.steps}
+            if name in work and per_step > 0:
+                bound, amount = work[name]
+                ach = amount / (per_step * 1e-3) / (1e12 if bound == "tensor" else 1e9)
+                k.update(bound=bound, achieved=round(ach, 2), unit="TFLOP/s" if bound == "tensor" else "GB/s",
+                         frac=round(ach / peaks[bound], 4))
+            kernels[name] = k
+        top = max((n for n in kernels if "bound" in kernels[n]), key=lambda n: kernels[n]["ms_per_step"])
+        tk = kernels[top]
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(top)
+        except Exception:
+            pass
+        roofline = {"kernel": top, "bound": tk["bound"], "achieved": tk["achieved"], "peak": peaks[tk["bound"]],
+                    "unit": tk["unit"], "frac": tk["frac"], "traffic": traffic,
+                    "peak_source": f"{peaks['source']} ({'sustained bf16' if tk['bound'] == 'tensor' else 'copy'})",
+                    "share_of_step": round(tk["ms_per_step"] / (ms / args.steps), 4)}
+        line = {"metric": METRIC, "value": b * world * args.steps / (ms * 1e-3), "unit": "clips/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+                "config": workload_config(b, precision), "clocks": clocks,
+                "e2e": {"value": b * world * args.steps / (ms_e2e * 1e-3), "unit": "clips/s",
+                        "h2d_bytes_per_step": rough_host.numel() * 4 + margin_host.numel() * 8,
+                        "d2h_bytes_per_step": preds_host.numel() * 4 + vals_host.numel() * 4,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels}
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_reference(args.cpu_clips, 3, 1)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

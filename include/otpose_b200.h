@@ -1,0 +1,171 @@
+/*
+ * otpose_b200 -- C ABI of the B200-native OTPose temporal fusion head.
+ *
+ * Plain C: device pointers, sizes, a CUDA stream handle.  No torch / ATen types.
+ * Every entry point returns an otp_status (0 == OK), never throws, never
+ * allocates device memory (scratch is passed in, sized by the matching
+ * *_workspace_bytes query) and enqueues its kernels on the given stream.
+ * otp_last_error() returns a thread-local description of the last failure.
+ *
+ * All tensors are contiguous fp32 in the reference's layouts (NCHW == (B,C,T)
+ * with T = H*W) unless stated.  File:line citations are relative to the
+ * reference tree (KyungMinJin/OTPose); each function names the reference
+ * interface it replaces.
+ */
+#ifndef OTPOSE_B200_H_
+#define OTPOSE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st *otp_stream_t; /* == cudaStream_t */
+
+typedef enum {
+  OTP_OK = 0,
+  OTP_ERR_ARG = 1,         /* bad shape / null pointer / misaligned buffer          */
+  OTP_ERR_UNSUPPORTED = 2, /* legal in the reference but not built here (see msg)   */
+  OTP_ERR_WORKSPACE = 3,   /* workspace too small                                   */
+  OTP_ERR_CUDA = 4         /* launch / runtime error (message has the CUDA string)  */
+} otp_status;
+
+typedef enum {
+  OTP_PREC_FP32 = 0, /* fp32 CUDA-core arithmetic everywhere (<=1e-3 vs reference)      */
+  OTP_PREC_BF16 = 1  /* bf16 operands on tcgen05 tensor cores, fp32 accumulate / LN /
+                        softmax / residual stream (<=2e-2 vs reference)               */
+} otp_precision;
+
+const char *otp_version(void);
+const char *otp_last_error(void);
+/* 1 if the current device is sm_100 (tcgen05 paths usable), 0 otherwise, <0 on error. */
+int otp_device_is_sm100(void);
+/* 1 if the tcgen05 (OTP_PREC_BF16) kernels are built into this library. */
+int otp_has_tensor_core_path(void);
+
+/* Launch accounting and optional per-kernel timing (CUDA events recorded on the
+ * launching stream around every kernel of this library while enabled).
+ *   otp_launch_count        kernels launched by this library since load
+ *   otp_profile_enable(1)   clear records and start recording; (0) stop
+ *   otp_profile_read        per kernel id: summed device ms and number of records;
+ *                           arrays of n >= otp_profile_num_kernels() entries     */
+unsigned long long otp_launch_count(void);
+int otp_profile_num_kernels(void);
+const char *otp_profile_kernel_name(int id);
+int otp_profile_enable(int on);
+int otp_profile_read(float *total_ms, int *launches, int n);
+
+/* ---------------------------------------------------------------------------
+ * a11  get_max_preds / get_final_preds / transform_preds
+ * replaces utils/heatmap.py:108-171 + utils/transform.py:76-126 (NumPy on host).
+ * heatmaps (N,J,H,W); center, scale (N,2) fp32 (only scale[:,0] is used, as in
+ * the reference).  Outputs (all device, any may be NULL):
+ *   out_idx     (N,J)   int32 flat argmax, FIRST maximum on ties (np.argmax)
+ *   out_coords  (N,J,2) fp32 heat-map coords after the +-0.25 shift
+ *   out_preds   (N,J,2) fp32 image coords (get_final_preds()[0])
+ *   out_maxvals (N,J)   fp32 (get_final_preds()[1], shape (N,J,1))
+ * ------------------------------------------------------------------------- */
+int otp_final_preds(const float *heatmaps, int n, int j, int h, int w, const float *center,
+                    const float *scale, int32_t *out_idx, float *out_coords, float *out_preds,
+                    float *out_maxvals, otp_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * a9  modulated deformable convolution forward
+ * replaces modulated_deform_conv_cuda_forward (thirdparty/deform_conv/src/
+ * deform_conv_cuda.cpp:474-549) and its im2col kernel (deform_conv_cuda_kernel.cu
+ * :402-432, 505-571) -- im2col, weight contraction and bias fused, batch in one
+ * launch, no `columns`/`ones` scratch.
+ *   x (B,C,H,W)  offset (B, dg*2*kh*kw, Ho, Wo)  mask (B, dg*kh*kw, Ho, Wo)
+ *   weight (Cout, C, kh, kw)  bias (Cout) or NULL  out (B,Cout,Ho,Wo)
+ * out = (accumulate ? out : 0) + alpha * (dcn(x) + bias); alpha/accumulate let
+ * the caller fuse the reference's 0.2-weighted sum over dilations
+ * (model/OTPose.py:387-392).  groups must be 1 (the only value OTPose uses).
+ * ------------------------------------------------------------------------- */
+int otp_mdcn_forward(const float *x, const float *offset, const float *mask, const float *weight,
+                     const float *bias, float *out, int b, int c, int h, int w, int cout, int kh,
+                     int kw, int stride, int pad, int dilation, int groups, int deformable_groups,
+                     float alpha, int accumulate, otp_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * a1  fusion prologue, replaces model/OTPose.py:320-330 and :339-359.
+ * rough (5B,J,T) ordered cur, prev, next, pprev, nnext.
+ *   otp_fusion_sum    -> total_b (B,J,T), squeezed (B,T)  [the reference's
+ *                        `squeezed` is this plane repeated J times]
+ *   otp_fusion_stack  -> x1, x2 (B, 8J, T) (channel j*8+m, OTPose.py:356-359)
+ *                        with the encoders' positional embedding already added
+ *                        (ConvVideoTransformer.py:140-155; pe1/pe2 (8J, >=T) with
+ *                        row stride pe_stride, NULL = no PE), intersection and
+ *                        prev_b (B,J,T).  margin (B,4) int64.
+ * ------------------------------------------------------------------------- */
+int otp_fusion_sum(const float *rough, int b, int j, int t, float *total_b, float *squeezed,
+                   otp_stream_t stream);
+int otp_fusion_stack(const float *rough, const int64_t *margin, const float *squeezed,
+                     const float *context, const float *pe1, const float *pe2, int pe_stride, int b,
+                     int j, int t, float *x1, float *x2, float *intersection, float *prev_b,
+                     otp_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * a2-a5  ConvTransformer building blocks, replaces model/blocks.py:95-110
+ * (LayerNorm), :264-279 (TransformerBlock.forward), :400-452 (MaskedMHCA.forward),
+ * :289-298 (AffineDropPath, eval) and ConvVideoTransformer.py:140-179.
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  /* reference state-dict entries of one TransformerBlock, device fp32 */
+  const float *ln1_w, *ln1_b, *ln2_w, *ln2_b;                   /* (1,C,1)            */
+  const float *q_conv_w, *k_conv_w, *v_conv_w;                  /* (C,1,3) depthwise   */
+  const float *q_norm_w, *q_norm_b, *k_norm_w, *k_norm_b, *v_norm_w, *v_norm_b;
+  const float *q_w, *q_b, *k_w, *k_b, *v_w, *v_b, *proj_w, *proj_b; /* (C,C,1), (C)    */
+  const float *mlp0_w, *mlp0_b, *mlp3_w, *mlp3_b;               /* (4C,C,1),(4C),(C,4C,1),(C) */
+  const float *scale_attn, *scale_mlp;                          /* (1,C,1) or NULL (=1) */
+} otp_block_params;
+
+/* Packed (transposed / padded / bf16) copy of one block's weights. */
+size_t otp_block_packed_bytes(int c, int n_head);
+int otp_block_pack(const otp_block_params *p, int c, int n_head, void *packed, size_t packed_bytes,
+                   otp_stream_t stream);
+
+/* y (B,C,T') = TransformerBlock(x (B,C,T)), T' = T for stride 1, (T-1)/2+1 for
+ * stride 2 (depthwise k=3 pad=1 stride 2 + MaxPool1d(3,2,1) skip).  Eval-mode
+ * semantics (dropout / drop-path inactive).  x and y must not alias. */
+size_t otp_block_workspace_bytes(int b, int c, int t, int n_head, int stride, int precision);
+int otp_block_forward(const void *packed, const float *x, float *y, int b, int c, int t, int n_head,
+                      int stride, int precision, void *workspace, size_t workspace_bytes,
+                      otp_stream_t stream);
+
+/* y = x + pe[:, :t]   (x,y (B,C,T); pe (C, >=T), row stride pe_stride) */
+int otp_add_pos_embd(const float *x, const float *pe, int pe_stride, float *y, int b, int c, int t,
+                     otp_stream_t stream);
+/* nn.Upsample(scale_factor=scale, mode='linear'), align_corners=False:
+ * x (B,C,Tin) -> y (B,C,Tin*scale)   (ConvVideoTransformer.py:108, 179) */
+int otp_upsample_linear(const float *x, float *y, int b, int c, int t_in, int scale,
+                        otp_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * a6  stack/view + final_layer (1x1 conv over the 3-scale pyramid), replaces
+ * model/OTPose.py:362-373.  s0 (B,C,T), s1 (B,C,T1), s2 (B,C,T2) are the raw
+ * branch outputs; the x2 / x4 linear upsampling of s1 / s2 is applied on the fly.
+ * weight (Cout, 3C), bias (Cout); out has batch stride out_bstride elements so
+ * it can be a channel slice of the concatenated `branches` buffer.
+ * ------------------------------------------------------------------------- */
+int otp_pyramid_conv1x1(const float *s0, const float *s1, const float *s2, int b, int c, int t,
+                        int t1, int t2, const float *weight, const float *bias, int cout,
+                        float *out, long long out_bstride, otp_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * a7/a8  small-channel Conv2d (stride 1, square kernel k in {1,3}, dilation d,
+ * padding d*(k/2)), replaces the nn.Conv2d (+folded eval BatchNorm + ReLU) calls
+ * of model/RSB.py:106-139 and the offset/mask convs of model/OTPose.py:168-177.
+ *   y = act( conv(x [+ x_add]) + bias [+ residual] )
+ * x, x_add, residual, y are channel slices: (ptr, batch stride in elements).
+ * ------------------------------------------------------------------------- */
+int otp_conv2d(const float *x, long long x_bstride, const float *x_add, long long x_add_bstride,
+               const float *weight, const float *bias, const float *residual,
+               long long residual_bstride, float *y, long long y_bstride, int b, int cin, int h,
+               int w, int cout, int k, int dilation, int relu, otp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OTPOSE_B200_H_ */

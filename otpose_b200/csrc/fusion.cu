@@ -1,0 +1,218 @@
+// a1 / a6 and the encoder glue ops: fusion prologue, positional embedding add,
+// linear upsampling, and the 3-scale pyramid 1x1 conv.  All HBM-bound streaming
+// kernels: one thread per (clip, token), channel loop inside, so every global
+// access is a coalesced row segment of a (B,C,T) tensor.
+#include "common.cuh"
+
+namespace otp {
+
+constexpr int kFuThreads = 256;
+
+// model/OTPose.py:324-326 -- total_b = cur+prev+next+pprev+nnext, squeezed = sum_j total_b
+__global__ void __launch_bounds__(kFuThreads)
+fusion_sum_kernel(const float *__restrict__ rough, int B, int J, int T, float *__restrict__ total_b,
+                  float *__restrict__ squeezed) {
+  const int t = blockIdx.x * kFuThreads + threadIdx.x;
+  const int b = blockIdx.y;
+  if (t >= T) return;
+  const size_t fs = (size_t)B * J * T;  // frame stride
+  const float *__restrict__ r = rough + (size_t)b * J * T + t;
+  float sq = 0.f;
+  for (int j = 0; j < J; ++j) {
+    const float *rj = r + (size_t)j * T;
+    float tot = __ldg(rj) + __ldg(rj + fs) + __ldg(rj + 2 * fs) + __ldg(rj + 3 * fs) + __ldg(rj + 4 * fs);
+    total_b[((size_t)b * J + j) * T + t] = tot;
+    sq += tot;
+  }
+  squeezed[(size_t)b * T + t] = sq;
+}
+
+// model/OTPose.py:330, 339-359 (+ pos_embd add of ConvVideoTransformer.py:140-155)
+__global__ void __launch_bounds__(kFuThreads)
+fusion_stack_kernel(const float *__restrict__ rough, const int64_t *__restrict__ margin,
+                    const float *__restrict__ squeezed, const float *__restrict__ context,
+                    const float *__restrict__ pe1, const float *__restrict__ pe2, int pe_stride, int B,
+                    int J, int T, float *__restrict__ x1, float *__restrict__ x2,
+                    float *__restrict__ intersection, float *__restrict__ prev_b_out) {
+  const int t = blockIdx.x * kFuThreads + threadIdx.x;
+  const int b = blockIdx.y;
+  if (t >= T) return;
+  const size_t fs = (size_t)B * J * T;
+  const float d0 = (float)(margin[4 * b + 0] + 1), d1 = (float)(margin[4 * b + 1] + 1);
+  const float d2 = (float)(margin[4 * b + 2] + 1), d3 = (float)(margin[4 * b + 3] + 1);
+  const float sq = __ldg(squeezed + (size_t)b * T + t);
+  for (int j = 0; j < J; ++j) {
+    const size_t o17 = ((size_t)b * J + j) * T + t;
+    const float *rj = rough + o17;
+    float cur = __ldg(rj), prev = __ldg(rj + fs), next = __ldg(rj + 2 * fs);
+    float pprev = __ldg(rj + 3 * fs), nnext = __ldg(rj + 4 * fs);
+    float inter = (cur + prev + next + pprev + nnext) * sq;
+    float ctx = __ldg(context + o17);
+    prev = prev / d0;
+    next = next / d1;
+    pprev = pprev / d2;
+    nnext = nnext / d3;
+    float prev_b = cur + (prev + pprev), next_b = cur + (next + nnext);
+    float close_b = cur + (next + prev), far_b = cur + (nnext + pprev);
+    float v1[8] = {inter, ctx, prev_b, far_b, close_b, prev_b * sq, far_b * sq, close_b * sq};
+    float v2[8] = {inter, ctx, next_b, close_b, far_b, next_b * sq, close_b * sq, far_b * sq};
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int c = j * 8 + m;
+      const size_t o = ((size_t)b * J * 8 + c) * T + t;
+      x1[o] = v1[m] + (pe1 ? __ldg(pe1 + (size_t)c * pe_stride + t) : 0.f);
+      x2[o] = v2[m] + (pe2 ? __ldg(pe2 + (size_t)c * pe_stride + t) : 0.f);
+    }
+    if (intersection) intersection[o17] = inter;
+    if (prev_b_out) prev_b_out[o17] = prev_b;
+  }
+}
+
+__global__ void __launch_bounds__(kFuThreads)
+add_pe_kernel(const float *__restrict__ x, const float *__restrict__ pe, int pe_stride,
+              float *__restrict__ y, int C, int T) {
+  const int t = blockIdx.x * kFuThreads + threadIdx.x;
+  if (t >= T) return;
+  const int c = blockIdx.y, b = blockIdx.z;
+  const size_t o = ((size_t)b * C + c) * T + t;
+  y[o] = __ldg(x + o) + __ldg(pe + (size_t)c * pe_stride + t);
+}
+
+// upsample_linear1d, align_corners=False, integer scale factor
+__device__ __forceinline__ void lerp_index(int d, float inv_scale, int L, int &i0, int &i1, float &l1) {
+  float src = inv_scale * ((float)d + 0.5f) - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  i0 = (int)src;
+  i1 = i0 + (i0 < L - 1 ? 1 : 0);
+  l1 = src - (float)i0;
+}
+
+__global__ void __launch_bounds__(kFuThreads)
+upsample_kernel(const float *__restrict__ x, float *__restrict__ y, int Tin, int scale) {
+  const int Tout = Tin * scale;
+  const int d = blockIdx.x * kFuThreads + threadIdx.x;
+  if (d >= Tout) return;
+  const size_t row = (size_t)blockIdx.z * gridDim.y + blockIdx.y;
+  int i0, i1;
+  float l1;
+  lerp_index(d, 1.0f / (float)scale, Tin, i0, i1, l1);
+  const float *xr = x + row * Tin;
+  y[row * Tout + d] = (1.f - l1) * __ldg(xr + i0) + l1 * __ldg(xr + i1);
+}
+
+// model/OTPose.py:362-373: out[o,t] = bias[o] + sum_{s,c} W[o, s*C+c] * up_s(src_s)[c,t]
+template <int CO>
+__global__ void __launch_bounds__(kFuThreads)
+pyramid_conv_kernel(const float *__restrict__ s0, const float *__restrict__ s1,
+                    const float *__restrict__ s2, int C, int T, int T1, int T2,
+                    const float *__restrict__ weight, const float *__restrict__ bias, int Cout,
+                    float *__restrict__ out, long long out_bstride) {
+  extern __shared__ float ws[];  // [3C][CO]
+  const int co0 = blockIdx.z * CO;
+  for (int e = threadIdx.x; e < 3 * C * CO; e += kFuThreads) {
+    int o = e % CO, k = e / CO;
+    ws[e] = (co0 + o < Cout) ? __ldg(weight + (size_t)(co0 + o) * 3 * C + k) : 0.f;
+  }
+  __syncthreads();
+  const int t = blockIdx.x * kFuThreads + threadIdx.x;
+  const int b = blockIdx.y;
+  if (t >= T) return;
+  float acc[CO];
+#pragma unroll
+  for (int o = 0; o < CO; ++o) acc[o] = 0.f;
+  int a0, a1, b0, b1;
+  float la, lb;
+  lerp_index(t, 0.5f, T1, a0, a1, la);
+  lerp_index(t, 0.25f, T2, b0, b1, lb);
+  const float *p0 = s0 + (size_t)b * C * T + t;
+  const float *p1 = s1 + (size_t)b * C * T1;
+  const float *p2 = s2 + (size_t)b * C * T2;
+  for (int c = 0; c < C; ++c) {
+    float v0 = __ldg(p0 + (size_t)c * T);
+    float v1 = (1.f - la) * __ldg(p1 + (size_t)c * T1 + a0) + la * __ldg(p1 + (size_t)c * T1 + a1);
+    float v2 = (1.f - lb) * __ldg(p2 + (size_t)c * T2 + b0) + lb * __ldg(p2 + (size_t)c * T2 + b1);
+    const float *w0 = ws + c * CO, *w1 = ws + (C + c) * CO, *w2 = ws + (2 * C + c) * CO;
+#pragma unroll
+    for (int o = 0; o < CO; ++o) acc[o] = fmaf(w0[o], v0, fmaf(w1[o], v1, fmaf(w2[o], v2, acc[o])));
+  }
+#pragma unroll
+  for (int o = 0; o < CO; ++o)
+    if (co0 + o < Cout)
+      out[(size_t)b * out_bstride + (size_t)(co0 + o) * T + t] = acc[o] + (bias ? __ldg(bias + co0 + o) : 0.f);
+}
+
+}  // namespace otp
+
+using namespace otp;
+
+extern "C" int otp_fusion_sum(const float *rough, int b, int j, int t, float *total_b, float *squeezed,
+                              otp_stream_t stream) {
+  OTP_REQUIRE(b >= 0 && j > 0 && t > 0 && b <= 65535);
+  if (b == 0) return OTP_OK;
+  OTP_REQUIRE(rough && total_b && squeezed);
+  LaunchScope ls(K_FUSION_SUM, (cudaStream_t)stream);
+  fusion_sum_kernel<<<dim3(ceil_div(t, kFuThreads), b), kFuThreads, 0, (cudaStream_t)stream>>>(
+      rough, b, j, t, total_b, squeezed);
+  return check_launch("fusion_sum_kernel");
+}
+
+extern "C" int otp_fusion_stack(const float *rough, const int64_t *margin, const float *squeezed,
+                                const float *context, const float *pe1, const float *pe2, int pe_stride,
+                                int b, int j, int t, float *x1, float *x2, float *intersection,
+                                float *prev_b, otp_stream_t stream) {
+  OTP_REQUIRE(b >= 0 && j > 0 && t > 0 && b <= 65535);
+  if (b == 0) return OTP_OK;
+  OTP_REQUIRE(rough && margin && squeezed && context && x1 && x2);
+  OTP_REQUIRE((!pe1 && !pe2) || pe_stride >= t);
+  LaunchScope ls(K_FUSION_STACK, (cudaStream_t)stream);
+  fusion_stack_kernel<<<dim3(ceil_div(t, kFuThreads), b), kFuThreads, 0, (cudaStream_t)stream>>>(
+      rough, margin, squeezed, context, pe1, pe2, pe_stride, b, j, t, x1, x2, intersection, prev_b);
+  return check_launch("fusion_stack_kernel");
+}
+
+extern "C" int otp_add_pos_embd(const float *x, const float *pe, int pe_stride, float *y, int b, int c,
+                                int t, otp_stream_t stream) {
+  OTP_REQUIRE(b >= 0 && c > 0 && t > 0 && b <= 65535 && c <= 65535 && pe_stride >= t);
+  if (b == 0) return OTP_OK;
+  OTP_REQUIRE(x && pe && y);
+  LaunchScope ls(K_ADD_PE, (cudaStream_t)stream);
+  add_pe_kernel<<<dim3(ceil_div(t, kFuThreads), c, b), kFuThreads, 0, (cudaStream_t)stream>>>(
+      x, pe, pe_stride, y, c, t);
+  return check_launch("add_pe_kernel");
+}
+
+extern "C" int otp_upsample_linear(const float *x, float *y, int b, int c, int t_in, int scale,
+                                   otp_stream_t stream) {
+  OTP_REQUIRE(b >= 0 && c > 0 && t_in > 0 && scale >= 1 && b <= 65535 && c <= 65535);
+  if (b == 0) return OTP_OK;
+  OTP_REQUIRE(x && y);
+  LaunchScope ls(K_UPSAMPLE, (cudaStream_t)stream);
+  upsample_kernel<<<dim3(ceil_div(t_in * scale, kFuThreads), c, b), kFuThreads, 0,
+                    (cudaStream_t)stream>>>(x, y, t_in, scale);
+  return check_launch("upsample_kernel");
+}
+
+extern "C" int otp_pyramid_conv1x1(const float *s0, const float *s1, const float *s2, int b, int c,
+                                   int t, int t1, int t2, const float *weight, const float *bias,
+                                   int cout, float *out, long long out_bstride, otp_stream_t stream) {
+  OTP_REQUIRE(b >= 0 && c > 0 && t > 0 && cout > 0 && b <= 65535);
+  OTP_REQUIRE(t1 * 2 == t && t2 * 4 == t);
+  if (b == 0) return OTP_OK;
+  OTP_REQUIRE(s0 && s1 && s2 && weight && out);
+  cudaStream_t st = (cudaStream_t)stream;
+  LaunchScope ls(K_PYRAMID, st);
+  if (cout % 17 == 0) {
+    size_t smem = (size_t)3 * c * 17 * sizeof(float);
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(pyramid_conv_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    pyramid_conv_kernel<17><<<dim3(ceil_div(t, kFuThreads), b, cout / 17), kFuThreads, smem, st>>>(
+        s0, s1, s2, c, t, t1, t2, weight, bias, cout, out, out_bstride);
+  } else {
+    size_t smem = (size_t)3 * c * 16 * sizeof(float);
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(pyramid_conv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    pyramid_conv_kernel<16><<<dim3(ceil_div(t, kFuThreads), b, ceil_div(cout, 16)), kFuThreads, smem, st>>>(
+        s0, s1, s2, c, t, t1, t2, weight, bias, cout, out, out_bstride);
+  }
+  return check_launch("pyramid_conv_kernel");
+}

@@ -1,0 +1,218 @@
+"""Drop-in ``OTPose`` for the temporal fusion head (reference model/OTPose.py:180-257
+constructor / state-dict layout, :307-394 forward).
+
+Everything after the backbone runs in the CUDA kernels behind the C ABI:
+
+    rough_heatmaps (5B,J,H,W), margin (B,4)
+      -> otp_fusion_sum                       total_b, squeezed           (OTPose.py:324-326)
+      -> flow_encoder (6 fused blocks, C=J)   context_encoding             (:331-335)
+      -> otp_fusion_stack                     x1, x2 (+pos_embd), intersection, prev_b (:330-359)
+      -> temporal_encoder1/2 (6+2 blocks)     3-scale pyramids             (:360-361)
+      -> otp_pyramid_conv1x1 x2               branches (upsample + stack + final_layer fused) (:362-375)
+      -> def_fuse, offset_mask_combine_conv   RSB chains via otp_conv2d    (:376-378)
+      -> per dilation: offset conv, mask conv, otp_mdcn_forward accumulating 0.2*dcn (:381-392)
+
+The HRNet backbone is out of scope (cuDNN convolutions): pass any
+module producing (5B, J, H, W) heat maps as ``backbone`` to use ``forward``;
+``forward_head`` is the hot path itself.
+"""
+from __future__ import annotations
+
+import logging
+
+import torch
+from torch import nn
+
+from .. import _lib
+from .ConvVideoTransformer import ConvTransformer
+from .RSB import CHAIN_RSB_BLOCKS
+from .layers import DeformableCONV
+from ..thirdparty.deform_conv import ModulatedDeformConv
+
+logger = logging.getLogger(__name__)
+
+
+class AttrDict(dict):
+    """Minimal yacs-CfgNode stand-in: attribute and item access."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+
+def default_cfg(heatmap_hw=(96, 72), num_joints=17, dilations=(3, 6, 9, 12, 15)):
+    """The head-relevant keys of configs/17/model_RSN.yaml + configs/default.py."""
+    h, w = heatmap_hw
+    return AttrDict(MODEL=AttrDict(
+        EXTRA=AttrDict(FINAL_CONV_KERNEL=1, PRETRAINED_LAYERS=["*"]),
+        HEATMAP_SIZE=[w, h], NUM_JOINTS=num_joints, FREEZE_HRNET_WEIGHTS=True, PRETRAINED="",
+        DEFORMABLE_CONV=AttrDict(DILATION=list(dilations), AGGREGATION_TYPE="weighted_sum"),
+        DEFORMABLE_CONV_CH=32, OFFSET_MASK_COMBINE_CONV=2))
+
+
+def _mask_conv(nc, kh, kw, dd, dg):
+    return nn.Conv2d(nc, dg * 1 * kh * kw, kernel_size=(3, 3), stride=(1, 1), dilation=(dd, dd),
+                     padding=(1 * dd, 1 * dd), bias=False)
+
+
+def _offset_conv(nc, kh, kw, dd, dg):
+    return nn.Conv2d(nc, dg * 2 * kh * kw, kernel_size=(3, 3), stride=(1, 1), dilation=(dd, dd),
+                     padding=(1 * dd, 1 * dd), bias=False)
+
+
+class OTPose(nn.Module):
+    def __init__(self, cfg, backbone=None, precision="fp32", **kwargs):
+        super().__init__()
+        extra = cfg['MODEL']['EXTRA']
+        self.num_frames = 8
+        self.pe_w, self.pe_h = cfg.MODEL.HEATMAP_SIZE
+        self.num_joints = cfg.MODEL.NUM_JOINTS
+        self.patch_size = 1
+        self.num_patches = self.pe_h * self.pe_w
+        self.patch_dim = self.num_joints
+        self.temporal_encoding_dim = self.patch_dim * self.num_frames
+        self.precision = precision
+        if extra['FINAL_CONV_KERNEL'] != 1:
+            raise NotImplementedError("final_layer kernels are built for FINAL_CONV_KERNEL = 1")
+        if backbone is not None:
+            self.rough_pose_estimation_net = backbone
+
+        self.scale_arch = (0, 6, 2)
+        self.flow_scale_arch = (0, 6, 0)
+        self.max_seq_len = self.num_patches
+        d = self.temporal_encoding_dim
+        self.temporal_encoder1 = ConvTransformer(d, d, n_head=2, n_embd_ks=3, max_len=self.num_patches,
+                                                 arch=self.scale_arch, proj_pdrop=0.1, path_pdrop=0.1,
+                                                 h=self.pe_h, precision=precision)
+        self.temporal_encoder2 = ConvTransformer(d, d, n_head=2, n_embd_ks=3, max_len=self.num_patches,
+                                                 arch=self.scale_arch, proj_pdrop=0.1, path_pdrop=0.1,
+                                                 h=self.pe_h, precision=precision)
+        self.flow_encoder = ConvTransformer(self.patch_dim, self.patch_dim, 1, 3, self.num_patches,
+                                            arch=self.flow_scale_arch, proj_pdrop=0.1, path_pdrop=0.1,
+                                            h=self.pe_h, precision=precision)
+        self.deformable_conv_dilations = list(cfg.MODEL.DEFORMABLE_CONV.DILATION)
+        self.deformable_aggregation_type = cfg.MODEL.DEFORMABLE_CONV.AGGREGATION_TYPE
+        if self.deformable_aggregation_type != "weighted_sum":
+            raise NotImplementedError("only AGGREGATION_TYPE = weighted_sum defines an output (OTPose.py:387)")
+        self.final_layer1 = nn.Conv2d(d * 3, self.num_joints, kernel_size=1, stride=1, padding=0)
+        self.final_layer2 = nn.Conv2d(d * 3, self.num_joints, kernel_size=1, stride=1, padding=0)
+        self.pretrained_layers = extra['PRETRAINED_LAYERS']
+
+        k = 3
+        def_ch = cfg.MODEL.DEFORMABLE_CONV_CH
+        n_rsb = cfg.MODEL.OFFSET_MASK_COMBINE_CONV
+        self.offset_mask_combine_conv = CHAIN_RSB_BLOCKS(self.num_joints * 3, def_ch, n_rsb)
+        self.def_fuse = CHAIN_RSB_BLOCKS(self.num_joints, self.num_joints, n_rsb)
+        self.offsets_list = nn.ModuleList(
+            nn.Sequential(_offset_conv(def_ch, k, k, dd, self.num_joints)) for dd in self.deformable_conv_dilations)
+        self.masks_list = nn.ModuleList(
+            nn.Sequential(_mask_conv(def_ch, k, k, dd, self.num_joints)) for dd in self.deformable_conv_dilations)
+        self.modulated_deform_conv_list = nn.ModuleList(
+            DeformableCONV(self.num_joints, k, dd) for dd in self.deformable_conv_dilations)
+        self.init_weights()
+
+    def init_weights(self):
+        """Head part of the reference init (model/OTPose.py:431-468)."""
+        for name, m in self.named_modules():
+            if name.split('.')[0] == "rough_pose_estimation_net":
+                continue
+            if isinstance(m, nn.Conv2d):
+                nn.init.normal_(m.weight, std=0.001)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+            elif isinstance(m, ModulatedDeformConv):
+                with torch.no_grad():
+                    m.weight.zero_()
+                    for k in range(m.weight.size(0)):
+                        m.weight[k, k, m.weight.size(2) // 2, m.weight.size(3) // 2] = 1.0
+                    if m.bias is not None:
+                        m.bias.zero_()
+
+    # ------------------------------------------------------------------
+    def forward(self, x, **kwargs):
+        """Reference signature: x (B, 15, Himg, Wimg), margin=(B, 4)."""
+        assert "margin" in kwargs
+        if not hasattr(self, "rough_pose_estimation_net"):
+            raise RuntimeError("OTPose was built without a backbone; call forward_head(rough_heatmaps, margin)")
+        x = torch.cat(x.split(3, dim=1), 0)
+        rough_heatmaps = self.rough_pose_estimation_net(x)
+        return self.forward_head(rough_heatmaps, kwargs["margin"])
+
+    @torch.no_grad()
+    def forward_head(self, rough_heatmaps, margin):
+        """model/OTPose.py:320-394.  rough_heatmaps (5B, J, H, W) fp32 CUDA ordered
+        cur, prev, next, pprev, nnext; margin (B, 4) integer.  Returns the reference
+        7-tuple.  ``squeezed`` is returned as a stride-0 expand of the (B,1,H,W) plane
+        (same values as the reference's J-fold stack)."""
+        if self.training:
+            raise NotImplementedError("CUDA OTPose head implements eval-mode forward; call .eval()")
+        _lib.require_cuda(rough_heatmaps)
+        lib = _lib.load()
+        rough = rough_heatmaps
+        if rough.dtype != torch.float32 or not rough.is_contiguous():
+            rough = rough.float().contiguous()
+        n5, j, h, w = rough.shape
+        assert n5 % 5 == 0 and j == self.num_joints and (h, w) == (self.pe_h, self.pe_w)
+        b, t, dev = n5 // 5, h * w, rough.device
+        if t % 4 != 0:
+            raise ValueError("H*W must be divisible by 4 (two stride-2 branch levels are upsampled back)")
+        margin = margin.to(device=dev, dtype=torch.int64).contiguous()
+        f32 = dict(dtype=torch.float32, device=dev)
+        c8 = self.temporal_encoding_dim
+        total_b = torch.empty((b, j, h, w), **f32)
+        squeezed = torch.empty((b, 1, h, w), **f32)
+        intersection = torch.empty((b, j, h, w), **f32)
+        prev_b = torch.empty((b, j, h, w), **f32)
+        out = torch.empty((b, j, h, w), **f32)
+        if b == 0:
+            ctx = torch.empty((b, j, h, w), **f32)
+            return out, rough_heatmaps, intersection, prev_b, ctx, squeezed.expand(b, j, h, w), total_b
+        st = _lib.stream_ptr(dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.otp_fusion_sum(_lib.dptr(rough), b, j, t, total_b.data_ptr(), squeezed.data_ptr(), st),
+                       "otp_fusion_sum")
+            ctx = self.flow_encoder(total_b)[0]                                  # (B, J, T)
+            x1 = torch.empty((b, c8, t), **f32)
+            x2 = torch.empty((b, c8, t), **f32)
+            pe1, ps1 = self.temporal_encoder1.pos_embd_for(t)
+            pe2, ps2 = self.temporal_encoder2.pos_embd_for(t)
+            assert ps1 == ps2
+            _lib.check(lib.otp_fusion_stack(
+                _lib.dptr(rough), margin.data_ptr(), squeezed.data_ptr(), _lib.dptr(ctx),
+                _lib.dptr(pe1, allow_none=True), _lib.dptr(pe2, allow_none=True), ps1, b, j, t,
+                x1.data_ptr(), x2.data_ptr(), intersection.data_ptr(), prev_b.data_ptr(), st), "otp_fusion_stack")
+            cat = torch.empty((b, 3 * j, h, w), **f32)       # [final_layer1 | final_layer2 | def_heatmaps]
+            for i, (enc, fl, xin) in enumerate(((self.temporal_encoder1, self.final_layer1, x1),
+                                                (self.temporal_encoder2, self.final_layer2, x2))):
+                s0, s1, s2 = enc.forward_tokens(xin)
+                _lib.check(lib.otp_pyramid_conv1x1(
+                    _lib.dptr(s0), _lib.dptr(s1), _lib.dptr(s2), b, c8, t, s1.shape[-1], s2.shape[-1],
+                    _lib.dptr(fl.weight.detach().view(j, 3 * c8)), _lib.dptr(fl.bias.detach()), j,
+                    cat.data_ptr() + 4 * i * j * t, 3 * j * t, st), "otp_pyramid_conv1x1")
+                del s0, s1, s2
+            del x1, x2
+            def_heatmaps = self.def_fuse(total_b)
+            cat[:, 2 * j:].copy_(def_heatmaps)
+            trans = self.offset_mask_combine_conv(cat)
+            cdef = trans.shape[1]
+            k2 = 9
+            offsets = torch.empty((b, 2 * k2 * j, h, w), **f32)
+            masks = torch.empty((b, k2 * j, h, w), **f32)
+            ww = 1.0 / len(self.deformable_conv_dilations)
+            for i, dd in enumerate(self.deformable_conv_dilations):
+                for conv, dst in ((self.offsets_list[i][0], offsets), (self.masks_list[i][0], masks)):
+                    _lib.check(lib.otp_conv2d(
+                        _lib.dptr(trans), cdef * t, None, 0, _lib.dptr(conv.weight.detach()), None, None, 0,
+                        dst.data_ptr(), dst.shape[1] * t, b, cdef, h, w, dst.shape[1], 3, dd, 0, st), "otp_conv2d")
+                dcn = self.modulated_deform_conv_list[i].deform_conv
+                from ..thirdparty.deform_conv import modulated_deform_conv
+                modulated_deform_conv(def_heatmaps, offsets, masks, dcn.weight, dcn.bias, dcn.stride,
+                                      dcn.padding, dcn.dilation, dcn.groups, dcn.deformable_groups,
+                                      alpha=ww, out=out, accumulate=(i > 0))
+        return (out, rough_heatmaps, intersection, prev_b, ctx.view(b, j, h, w),
+                squeezed.expand(b, j, h, w), total_b)

@@ -1,0 +1,139 @@
+"""Drop-in ``CHAIN_RSB_BLOCKS`` / ``RSB_BLOCK`` / ``conv_bn_relu`` (reference
+model/RSB.py:10-139) -- same constructors and state-dict keys; eval-mode forward
+through ``otp_conv2d`` with BatchNorm folded into the conv weights and the
+branch adds / residual / ReLU / channel concat fused into the conv launches.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from .. import _lib
+
+__all__ = ["RSB_BLOCK", "CHAIN_RSB_BLOCKS", "conv_bn_relu"]
+
+
+class conv_bn_relu(nn.Module):
+    def __init__(self, in_planes, out_planes, kernel_size, stride, padding, has_bn=True, has_relu=True,
+                 efficient=False, groups=1):
+        super().__init__()
+        if stride != 1 or groups != 1 or kernel_size not in (1, 3) or padding != kernel_size // 2:
+            raise NotImplementedError("conv_bn_relu kernels: stride 1, groups 1, k in {1,3}, 'same' padding")
+        self.conv = nn.Conv2d(in_planes, out_planes, kernel_size=kernel_size, stride=stride, padding=padding,
+                              groups=groups)
+        self.has_bn, self.has_relu, self.efficient = has_bn, has_relu, efficient
+        self.bn = nn.BatchNorm2d(out_planes)
+        self.relu = nn.ReLU(inplace=True)
+        self.kernel_size = kernel_size
+        self._folded = None
+        self._folded_key = None
+
+    def folded(self):
+        """(weight, bias) with the eval-mode BatchNorm affine folded in (RSB.py:120-131)."""
+        ps = [self.conv.weight, self.conv.bias, self.bn.weight, self.bn.bias, self.bn.running_mean,
+              self.bn.running_var]
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if self._folded is None or key != self._folded_key:
+            with torch.no_grad():
+                w, b = self.conv.weight.detach().float(), self.conv.bias.detach().float()
+                if self.has_bn:
+                    g = self.bn.weight.detach() / torch.sqrt(self.bn.running_var + self.bn.eps)
+                    w = w * g.view(-1, 1, 1, 1)
+                    b = (b - self.bn.running_mean) * g + self.bn.bias.detach()
+                self._folded = (w.contiguous(), b.contiguous())
+            self._folded_key = key
+        return self._folded
+
+    def run(self, x, x_bs, out, out_bs, b, h, w, x_add=None, x_add_bs=0, residual=None, residual_bs=0,
+            relu=None):
+        """Launch on raw (pointer, batch-stride) channel slices."""
+        wt, bias = self.folded()
+        relu = self.has_relu if relu is None else relu
+        lib = _lib.load()
+        _lib.check(lib.otp_conv2d(x, x_bs, x_add, x_add_bs, wt.data_ptr(), bias.data_ptr(), residual,
+                                  residual_bs, out, out_bs, b, self.conv.in_channels, h, w,
+                                  self.conv.out_channels, self.kernel_size, 1, int(relu),
+                                  _lib.stream_ptr(wt.device)), "otp_conv2d")
+
+    def forward(self, x):
+        if self.training:
+            raise NotImplementedError("CUDA conv_bn_relu implements eval-mode forward; call .eval()")
+        _lib.require_cuda(x)
+        b, c, h, w = x.shape
+        y = torch.empty((b, self.conv.out_channels, h, w), dtype=torch.float32, device=x.device)
+        if b:
+            with torch.cuda.device(x.device):
+                self.run(_lib.dptr(x), c * h * w, y.data_ptr(), y.shape[1] * h * w, b, h, w)
+        return y
+
+
+class RSB_BLOCK(nn.Module):
+    expansion = 1
+
+    def __init__(self, in_planes, planes, stride=1, groups=1, downsample=None, efficient=False):
+        super().__init__()
+        bc = self.branch_ch = in_planes * 26 // 64
+        self.conv_bn_relu1 = conv_bn_relu(in_planes, 4 * bc, 1, stride, 0, groups=groups)
+        for name in ("1_1", "2_1", "2_2", "3_1", "3_2", "3_3", "4_1", "4_2", "4_3", "4_4"):
+            setattr(self, "conv_bn_relu2_" + name, conv_bn_relu(bc, bc, 3, 1, 1, groups=groups))
+        self.conv_bn_relu3 = conv_bn_relu(4 * bc, planes * self.expansion, 1, 1, 0, groups=groups, has_relu=False)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = downsample
+        self.planes = planes
+
+    def forward(self, x):
+        """RSB.py:81-103.  Intermediate layout: `spx` (B,4bc,H,W) and one (B,10bc,H,W)
+        buffer holding the ten branch outputs; the concat (out_1_1, out_2_2, out_3_3,
+        out_4_4) is assembled by writing those four convs into a (B,4bc,H,W) buffer."""
+        if self.training:
+            raise NotImplementedError("CUDA RSB_BLOCK implements eval-mode forward; call .eval()")
+        _lib.require_cuda(x)
+        b, cin, h, w = x.shape
+        p = h * w
+        bc = self.branch_ch
+        dev = x.device
+        spx = torch.empty((b, 4 * bc, h, w), dtype=torch.float32, device=dev)
+        tmp = torch.empty((6, b, bc, h, w), dtype=torch.float32, device=dev)   # 2_1 3_1 3_2 4_1 4_2 4_3
+        cat = torch.empty((b, 4 * bc, h, w), dtype=torch.float32, device=dev)  # 1_1 2_2 3_3 4_4
+        out = torch.empty((b, self.planes, h, w), dtype=torch.float32, device=dev)
+        if b == 0:
+            return out
+        xp = _lib.dptr(x)
+        sp = lambda i: spx.data_ptr() + 4 * i * bc * p           # noqa: E731  channel slice i of spx
+        ct = lambda i: cat.data_ptr() + 4 * i * bc * p           # noqa: E731
+        tp = lambda i: tmp[i].data_ptr()                         # noqa: E731
+        S4, S1 = 4 * bc * p, bc * p
+        m = lambda n: getattr(self, "conv_bn_relu2_" + n)        # noqa: E731
+        with torch.cuda.device(dev):
+            self.conv_bn_relu1.run(xp, cin * p, spx.data_ptr(), S4, b, h, w)
+            m("1_1").run(sp(0), S4, ct(0), S4, b, h, w)                                  # out_1_1
+            m("2_1").run(sp(1), S4, tp(0), S1, b, h, w, x_add=ct(0), x_add_bs=S4)        # out_2_1
+            m("2_2").run(tp(0), S1, ct(1), S4, b, h, w)                                  # out_2_2
+            m("3_1").run(sp(2), S4, tp(1), S1, b, h, w, x_add=tp(0), x_add_bs=S1)        # out_3_1
+            m("3_2").run(tp(1), S1, tp(2), S1, b, h, w, x_add=ct(1), x_add_bs=S4)        # out_3_2
+            m("3_3").run(tp(2), S1, ct(2), S4, b, h, w)                                  # out_3_3
+            m("4_1").run(sp(3), S4, tp(3), S1, b, h, w, x_add=tp(1), x_add_bs=S1)        # out_4_1
+            m("4_2").run(tp(3), S1, tp(4), S1, b, h, w, x_add=tp(2), x_add_bs=S1)        # out_4_2
+            m("4_3").run(tp(4), S1, tp(5), S1, b, h, w, x_add=ct(2), x_add_bs=S4)        # out_4_3
+            m("4_4").run(tp(5), S1, ct(3), S4, b, h, w)                                  # out_4_4
+            if self.downsample is not None:
+                skip = self.downsample(x)
+                rp, rbs = skip.data_ptr(), self.planes * p
+            else:
+                rp, rbs = xp, cin * p
+            self.conv_bn_relu3.run(cat.data_ptr(), S4, out.data_ptr(), self.planes * p, b, h, w,
+                                   residual=rp, residual_bs=rbs, relu=True)
+        return out
+
+
+class CHAIN_RSB_BLOCKS(nn.Module):
+    def __init__(self, in_planes, out_planes, num_blocks, groups=1):
+        super().__init__()
+        ds = conv_bn_relu(in_planes, out_planes, kernel_size=1, stride=1, padding=0, has_relu=False, groups=groups)
+        layers = [RSB_BLOCK(in_planes, out_planes, 1, downsample=ds)]
+        for _ in range(1, num_blocks):
+            layers.append(RSB_BLOCK(out_planes, out_planes, 1, downsample=None))
+        self.layers = nn.Sequential(*layers)
+
+    def forward(self, x):
+        return self.layers(x)

@@ -1,0 +1,115 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every
+symbol the header declares, drop-in modules expose the reference's state-dict
+layout, argument validation / error behaviour, synthetic-data determinism."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from otpose_b200 import _lib
+from otpose_b200.model import ConvTransformer, OTPose, default_cfg
+from otpose_b200.model.RSB import CHAIN_RSB_BLOCKS
+from otpose_b200.utils import synthetic as syn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "otpose_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(otp_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    syms = header_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/otpose_b200.h but not exported"
+    assert set(syms) == set(_lib.SIGNATURES), "ctypes signatures out of sync with the header"
+    assert b"sm_100a" in lib.otp_version()
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libotpose_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU"):
+        _lib.load()
+
+
+def test_shape_queries_and_unsupported_widths():
+    lib = _lib.load()
+    assert lib.otp_block_packed_bytes(136, 2) > 4 * (3 * 136 * 136 + 8 * 136 * 136)
+    assert lib.otp_block_packed_bytes(17, 1) > 0
+    assert lib.otp_block_packed_bytes(100, 4) == 0
+    assert b"not built" in lib.otp_last_error()
+    assert lib.otp_block_workspace_bytes(2, 136, 48, 2, 1, 0) > 2 * 136 * 48 * 4
+    assert lib.otp_block_workspace_bytes(2, 136, 48, 2, 3, 0) == 0
+    # argument validation happens before any CUDA call
+    assert lib.otp_final_preds(None, 1, 17, 0, 4, None, None, None, None, None, None, None) == 1
+    assert lib.otp_mdcn_forward(None, None, None, None, None, None, 1, 17, 8, 8, 17, 3, 3, 1, 1, 1, 2, 17,
+                                1.0, 0, None) == 2
+    assert lib.otp_conv2d(None, 0, None, 0, None, None, None, 0, None, 0, 1, 4, 8, 8, 4, 5, 1, 0, None) == 2
+    # empty batches are a no-op, not an error (reference handles B=0 tensors)
+    assert lib.otp_final_preds(None, 0, 17, 8, 8, None, None, None, None, None, None, None) == 0
+    assert lib.otp_fusion_sum(None, 0, 17, 64, None, None, None) == 0
+
+
+def manifest():
+    with open(os.path.join(ROOT, "tests", "golden", "state_dict_manifest.json")) as f:
+        return json.load(f)
+
+
+def shapes(m):
+    return {k: list(v.shape) for k, v in m.state_dict().items()}
+
+
+def test_state_dict_layout_matches_reference():
+    man = manifest()
+    enc = ConvTransformer(136, 136, n_head=2, n_embd_ks=3, max_len=48, arch=(0, 6, 2), proj_pdrop=0.1,
+                          path_pdrop=0.1, h=8)
+    assert shapes(enc) == man["encoder_c136"]
+    flow = ConvTransformer(17, 17, 1, 3, 48, arch=(0, 6, 0), proj_pdrop=0.1, path_pdrop=0.1, h=8)
+    assert shapes(flow) == man["encoder_c17"]
+    assert shapes(CHAIN_RSB_BLOCKS(17, 17, 2)) == man["rsb_def_fuse"]
+    assert shapes(CHAIN_RSB_BLOCKS(51, 32, 2)) == man["rsb_combine"]
+    head = OTPose(default_cfg((16, 12)))
+    mine = {k: v for k, v in shapes(head).items() if "pos_embd" not in k}
+    assert mine == man["head"]
+    assert sum(p.numel() for p in OTPose(default_cfg((96, 72))).parameters()) == 4401878
+    # reference init: AffineDropPath scale 1e-4, DCN identity centre tap
+    assert torch.allclose(head.temporal_encoder1.stem[0].drop_path_attn.scale, torch.full((1, 136, 1), 1e-4))
+    w = head.modulated_deform_conv_list[0].deform_conv.weight
+    assert w[3, 3, 1, 1] == 1 and w.sum() == 17
+
+
+def test_pos_embd_matches_reference_table():
+    from oracle.head_oracle import sinusoid_encoding
+    enc = ConvTransformer(136, 136, 2, 3, 64, arch=(0, 1, 0), h=8)
+    assert torch.equal(enc.pos_embd, sinusoid_encoding(64, 136) / (136 ** 0.5))
+
+
+def test_cpu_tensors_are_rejected_like_the_reference():
+    from otpose_b200.thirdparty.deform_conv import ModulatedDeformConv
+    m = ModulatedDeformConv(17, 17, 3, padding=3, dilation=3, deformable_groups=17)
+    with pytest.raises(NotImplementedError):   # functions/deform_conv.py:131-132
+        m(torch.zeros(1, 17, 8, 8), torch.zeros(1, 306, 8, 8), torch.zeros(1, 153, 8, 8))
+    blk = ConvTransformer(17, 17, 1, 3, 64, arch=(0, 1, 0), h=8).eval()
+    with pytest.raises(NotImplementedError):
+        blk(torch.zeros(1, 17, 8, 8))
+    with pytest.raises(NotImplementedError):   # training-mode semantics are not built
+        ConvTransformer(17, 17, 1, 3, 64, arch=(0, 1, 0), h=8).train()(torch.zeros(1, 17, 8, 8))
+
+
+def test_synthetic_is_deterministic_and_nontrivial():
+    a = syn.synth_tensor("temporal_encoder1.stem.0.drop_path_attn.scale", (1, 136, 1))
+    b = syn.synth_tensor("temporal_encoder1.stem.0.drop_path_attn.scale", (1, 136, 1))
+    assert torch.equal(a, b) and a.min() >= 0.5 and a.max() <= 1.5
+    r = syn.synth_rough_heatmaps(2, 17, 24, 18)
+    assert r.shape == (10, 17, 24, 18) and torch.equal(r, syn.synth_rough_heatmaps(2, 17, 24, 18))
+    assert 0.2 < r.amax() < 1.2
+    m = syn.synth_margin(64)
+    assert m.dtype == torch.int64 and set(np.unique(m.numpy())) <= {0, 1, 2}
