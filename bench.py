@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="person-clips per GPU per step")
-    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16", "fp16"])
     ap.add_argument("--cpu-clips", type=int, default=2, help="clips per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -226,7 +226,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     precision = args.precision
     if precision == "auto":
-        precision = "bf16" if lib.otp_has_tensor_core_path() else "fp32"
+        precision = "fp16" if lib.otp_has_tensor_core_path() else "fp32"
     b = args.batch
 
     model = OTPose(default_cfg((H, W)), precision=precision)
@@ -314,7 +314,7 @@ def run_b200(args):
         line = {"metric": METRIC, "value": b * world * args.steps / (ms * 1e-3), "unit": "clips/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+                "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[precision], "data": "synthetic",
                 "config": workload_config(b, precision), "clocks": clocks,
                 "e2e": {"value": b * world * args.steps / (ms_e2e * 1e-3), "unit": "clips/s",
                         "h2d_bytes_per_step": rough_host.numel() * 4 + margin_host.numel() * 8,

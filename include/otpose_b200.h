@@ -34,8 +34,10 @@ typedef enum {
 
 typedef enum {
   OTP_PREC_FP32 = 0, /* fp32 CUDA-core arithmetic everywhere (<=1e-3 vs reference)      */
-  OTP_PREC_BF16 = 1  /* bf16 operands on tcgen05 tensor cores, fp32 accumulate / LN /
-                        softmax / residual stream (<=2e-2 vs reference)               */
+  OTP_PREC_BF16 = 1, /* bf16 operands on tcgen05 tensor cores, fp32 accumulate / LN /
+                        softmax / residual stream                                     */
+  OTP_PREC_FP16 = 2  /* same kernels with IEEE-half operands: same speed, 8x finer operand
+                        rounding (<=2e-2 vs reference with margin)                    */
 } otp_precision;
 
 const char *otp_version(void);
@@ -164,6 +166,17 @@ int otp_conv2d(const float *x, long long x_bstride, const float *x_add, long lon
                const float *weight, const float *bias, const float *residual,
                long long residual_bstride, float *y, long long y_bstride, int b, int cin, int h,
                int w, int cout, int k, int dilation, int relu, otp_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Self-test of the tcgen05 / TMEM plumbing (no reference counterpart): one CTA
+ * computes D[128,n] (fp32, row-major) = A . B^T over `ksteps` K=16 steps from
+ * caller-built bf16 shared-memory operand images and explicit UMMA descriptor
+ * fields (byte offsets; *_mn_major selects the MN-major operand view).
+ * ------------------------------------------------------------------------- */
+int otp_debug_umma_gemm(const void *a_img, int a_bytes, const void *b_img, int b_bytes, float *d, int n,
+                        int ksteps, unsigned a_off, unsigned a_lbo, unsigned a_sbo, unsigned a_kstep,
+                        unsigned b_off, unsigned b_lbo, unsigned b_sbo, unsigned b_kstep, int a_mn_major,
+                        int b_mn_major, int repeat, otp_stream_t stream);
 
 #ifdef __cplusplus
 }

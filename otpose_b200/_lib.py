@@ -13,8 +13,8 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libotpose_b200.so")
 
-PREC_FP32, PREC_BF16 = 0, 1
-_PREC = {"fp32": PREC_FP32, "bf16": PREC_BF16}
+PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2
+_PREC = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp16": PREC_FP16}
 
 vp, i32, i64, f32, sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
 
@@ -53,6 +53,7 @@ SIGNATURES = {
     "otp_pyramid_conv1x1": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, vp, i64, vp]),
     "otp_conv2d": (i32, [vp, i64, vp, i64, vp, vp, vp, i64, vp, i64, i32, i32, i32, i32, i32, i32, i32,
                          i32, vp]),
+    "otp_debug_umma_gemm": (i32, [vp, i32, vp, i32, vp, i32, i32] + [C.c_uint] * 8 + [i32, i32, i32, vp]),
 }
 
 _lib = None
@@ -90,7 +91,7 @@ def precision_code(p) -> int:
     try:
         return _PREC[p]
     except KeyError:
-        raise ValueError(f"precision must be 'fp32' or 'bf16', got {p!r}") from None
+        raise ValueError(f"precision must be 'fp32', 'bf16' or 'fp16', got {p!r}") from None
 
 
 def dptr(t, dtype=torch.float32, allow_none=False):

@@ -11,7 +11,7 @@ size_t block_tc_packed_bytes(int c);
 int block_tc_pack(const otp_block_params *p, int c, void *packed_tc, cudaStream_t st);
 size_t block_tc_workspace_bytes(int b, int c, int t, int stride);
 int block_forward_tc(const void *packed_fp32, const void *packed_tc, const float *x, float *y, int b,
-                     int c, int t, int stride, void *ws_simt, void *ws_tc, cudaStream_t st);
+                     int c, int t, int stride, int f16, void *ws_tc, cudaStream_t st);
 
 static int check_shape(int c, int n_head) {
   if (!((c == 136 && n_head == 2) || (c == 17 && n_head == 1))) {
@@ -53,11 +53,14 @@ extern "C" int otp_block_pack(const otp_block_params *p, int c, int n_head, void
   return OTP_OK;
 }
 
+static bool use_tc(int c, int precision) {
+  return (precision == OTP_PREC_BF16 || precision == OTP_PREC_FP16) && block_tc_packed_bytes(c) > 0;
+}
+
 extern "C" size_t otp_block_workspace_bytes(int b, int c, int t, int n_head, int stride, int precision) {
   if (check_shape(c, n_head) != OTP_OK || b <= 0 || t <= 0 || (stride != 1 && stride != 2)) return 0;
-  size_t s = block_workspace(b, c, t, n_head, stride).total;
-  if (precision == OTP_PREC_BF16) s += block_tc_workspace_bytes(b, c, t, stride);
-  return s;
+  if (use_tc(c, precision)) return block_tc_workspace_bytes(b, c, t, stride);
+  return block_workspace(b, c, t, n_head, stride).total;
 }
 
 extern "C" int otp_block_forward(const void *packed, const float *x, float *y, int b, int c, int t,
@@ -66,7 +69,7 @@ extern "C" int otp_block_forward(const void *packed, const float *x, float *y, i
   if (int e = check_shape(c, n_head)) return e;
   OTP_REQUIRE(b >= 0 && t > 0 && b <= 65535);
   OTP_REQUIRE(stride == 1 || stride == 2);
-  OTP_REQUIRE(precision == OTP_PREC_FP32 || precision == OTP_PREC_BF16);
+  OTP_REQUIRE(precision == OTP_PREC_FP32 || precision == OTP_PREC_BF16 || precision == OTP_PREC_FP16);
   if (b == 0) return OTP_OK;
   OTP_REQUIRE(packed && x && y && workspace && x != y);
   OTP_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0);
@@ -76,12 +79,10 @@ extern "C" int otp_block_forward(const void *packed, const float *x, float *y, i
     return OTP_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (precision == OTP_PREC_BF16 && block_tc_packed_bytes(c) > 0) {
-    const size_t simt_ws = block_workspace(b, c, t, n_head, stride).total;
-    return block_forward_tc(packed, static_cast<const char *>(packed) + fp32_pack_bytes(c), x, y, b, c, t,
-                            stride, workspace, static_cast<char *>(workspace) + simt_ws, st);
-  }
+  if (use_tc(c, precision))
+    return block_forward_tc(packed, static_cast<const char *>(packed) + fp32_pack_bytes(c), x, y, b, c, t, stride,
+                            precision == OTP_PREC_FP16, workspace, st);
   // C = 17 (flow encoder, 0.6 % of the head's FLOPs) has no tensor-core shape:
-  // it runs the CUDA-core kernels in both precision modes.
+  // it runs the fp32 CUDA-core kernels in every precision mode.
   return block_forward_simt(packed, x, y, b, c, t, stride, workspace, st);
 }

@@ -144,7 +144,7 @@ class OTPose(nn.Module):
         return self.forward_head(rough_heatmaps, kwargs["margin"])
 
     @torch.no_grad()
-    def forward_head(self, rough_heatmaps, margin):
+    def forward_head(self, rough_heatmaps, margin, _debug=None):
         """model/OTPose.py:320-394.  rough_heatmaps (5B, J, H, W) fp32 CUDA ordered
         cur, prev, next, pprev, nnext; margin (B, 4) integer.  Returns the reference
         7-tuple.  ``squeezed`` is returned as a stride-0 expand of the (B,1,H,W) plane
@@ -199,6 +199,8 @@ class OTPose(nn.Module):
             def_heatmaps = self.def_fuse(total_b)
             cat[:, 2 * j:].copy_(def_heatmaps)
             trans = self.offset_mask_combine_conv(cat)
+            if _debug is not None:
+                _debug.update(cat=cat, trans=trans, def_heatmaps=def_heatmaps)
             cdef = trans.shape[1]
             k2 = 9
             offsets = torch.empty((b, 2 * k2 * j, h, w), **f32)
