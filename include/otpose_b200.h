@@ -168,6 +168,24 @@ int otp_conv2d(const float *x, long long x_bstride, const float *x_add, long lon
                int w, int cout, int k, int dilation, int relu, otp_stream_t stream);
 
 /* ---------------------------------------------------------------------------
+ * a8 + a9 + a10 fused (tensor-core precisions only): for one dilation d,
+ *   offsets = conv3x3_d(trans; w_off), masks = conv3x3_d(trans; w_msk),
+ *   out = (accumulate ? out : 0) + alpha * (modulated_dcn_d(x; offsets, masks; dcn_w) + dcn_b)
+ * replaces model/OTPose.py:381-392 for that dilation (two nn.Conv2d + the DCN op +
+ * the weighted sum) without materialising offsets / masks.  Built for the
+ * reference shapes: 17 joints (deformable groups), 32 feature channels, 3x3 taps.
+ *   w_off (306,32,3,3), w_msk (153,32,3,3) are packed once per dilation by
+ *   otp_offset_mask_pack into `packed` (otp_offset_mask_pack_bytes() bytes);
+ *   trans (B,32,H,W), x (B,17,H,W), dcn_w (17,17,3,3), dcn_b (17) or NULL, out (B,17,H,W).
+ * ------------------------------------------------------------------------- */
+size_t otp_offset_mask_pack_bytes(void);
+int otp_offset_mask_pack(const float *w_off, const float *w_msk, int joints, int cin, void *packed,
+                         size_t packed_bytes, otp_stream_t stream);
+int otp_offset_mask_dcn_forward(const void *packed, const float *trans, const float *x, const float *dcn_w,
+                                const float *dcn_b, float *out, int b, int h, int w, int dilation, float alpha,
+                                int accumulate, int precision, otp_stream_t stream);
+
+/* ---------------------------------------------------------------------------
  * Self-test of the tcgen05 / TMEM plumbing (no reference counterpart): one CTA
  * computes D[128,n] (fp32, row-major) = A . B^T over `ksteps` K=16 steps from
  * caller-built bf16 shared-memory operand images and explicit UMMA descriptor

@@ -53,6 +53,9 @@ SIGNATURES = {
     "otp_pyramid_conv1x1": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, vp, i64, vp]),
     "otp_conv2d": (i32, [vp, i64, vp, i64, vp, vp, vp, i64, vp, i64, i32, i32, i32, i32, i32, i32, i32,
                          i32, vp]),
+    "otp_offset_mask_pack_bytes": (sz, []),
+    "otp_offset_mask_pack": (i32, [vp, vp, i32, i32, vp, sz, vp]),
+    "otp_offset_mask_dcn_forward": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, i32, vp]),
     "otp_debug_umma_gemm": (i32, [vp, i32, vp, i32, vp, i32, i32] + [C.c_uint] * 8 + [i32, i32, i32, vp]),
 }
 

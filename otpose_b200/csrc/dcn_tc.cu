@@ -1,0 +1,276 @@
+// a8 + a9 + a10 fused (16-bit tensor-core path): dilated 3x3 offset conv (32 -> 306) and
+// mask conv (32 -> 153) as one implicit GEMM on tcgen05, consumed straight out of TMEM
+// by the modulated deformable convolution and the 0.2-weighted accumulation.
+//
+// Reference: model/OTPose.py:381-392 runs, per dilation, two cuDNN convs that write
+// offsets (B,306,H,W) and masks (B,153,H,W) to HBM -- 63 MB fp32 per clip over the five
+// dilations -- and the DCN op (thirdparty/deform_conv/src/deform_conv_cuda.cpp:474-549)
+// reads them back per sample.  Here those tensors never exist: a tile of 128 pixels
+// forms its im2col operand in shared memory (9 taps x [128 px][32 ch]), one UMMA chain
+// (M128 x N256 x K288) leaves the tile's offsets and masks in TMEM with pixel == TMEM
+// lane, and each thread reads its own pixel's 27 values per joint with tcgen05.ld,
+// samples def_heatmaps bilinearly (deform_conv_cuda_kernel.cu:402-432, 505-571 semantics)
+// and contracts with the 17x153 DCN weight.
+//
+// The 17 joints (deformable groups) are split 9 + 8 over two launches so that one
+// launch's conv weights (9 taps x [256][32] x 2 B = 144 KB) stay resident in shared
+// memory for a persistent CTA; the second launch adds its partial sums to the first
+// (stream-ordered, deterministic).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace otp {
+using namespace tc;
+
+namespace {
+constexpr int kJ = 17, kCin = 32, kTaps = 9;
+constexpr int kTM = 128, kThreads = 256;
+constexpr int kNPad = 256;                        // UMMA N (>= 27 * 9 = 243)
+constexpr uint32_t kCS = 128, kRS32 = (kCin / 8) * 128;   // 512
+constexpr uint32_t kATap = (kTM / 8) * kRS32;     // 8192   [128 px][32 ch]
+constexpr uint32_t kWTap = (kNPad / 8) * kRS32;   // 16384  [256 rows][32 ch]
+constexpr uint32_t kWSlice = kTaps * kWTap;       // 147456 one joint-half
+constexpr uint32_t kASlice = kTaps * kATap;       // 73728
+constexpr int kJ0[2] = {0, 9}, kNJ[2] = {9, 8};
+constexpr size_t kPackBytes = (size_t)2 * 2 * kWSlice;   // [format][joint half]
+constexpr size_t kSmem = (size_t)kWSlice + kASlice + (size_t)kJ * 81 * 4 + 64;
+static_assert(kSmem + 1024 <= 227 * 1024, "fused DCN shared memory");
+
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float &a, float &b) {
+  uint32_t r0, r1;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  a = __uint_as_float(r0);
+  b = __uint_as_float(r1);
+}
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, float &a) {
+  uint32_t r0;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r0) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  a = __uint_as_float(r0);
+}
+
+template <bool F16>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_dcn_fused_kernel(const uint8_t *__restrict__ wimg, const float *__restrict__ trans,
+                    const float *__restrict__ x, const float *__restrict__ dcn_w,
+                    const float *__restrict__ dcn_b, float *__restrict__ out, int B, int H, int W, int dil,
+                    int j0, int nj, float alpha, int accumulate, int tiles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t *ws = smem;                         // 9 x [256][32] conv weights, resident
+  uint8_t *as = smem + kWSlice;               // 9 x [128][32] im2col taps; later the partial-sum exchange
+  float *wd = reinterpret_cast<float *>(as + kASlice);   // [17][nj*9] DCN weight slice
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q4 = warp & 3, half = warp >> 2, tok = q4 * 32 + lane;
+  const int P = H * W;
+
+  for (uint32_t o = threadIdx.x * 16; o < kWSlice; o += kThreads * 16) cp_async16(ws + o, wimg + o);
+  cp_async_commit();
+  for (int e = threadIdx.x; e < kJ * nj * 9; e += kThreads) {
+    const int o = e / (nj * 9), r = e % (nj * 9);
+    wd[o * 81 + r] = dcn_w[(size_t)o * kJ * 9 + j0 * 9 + r];
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  cp_async_wait<0>();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = tmem_slot;
+  const uint32_t idesc = make_idesc_16(kNPad, false, false, F16 ? 0u : 1u);
+  uint32_t ph = 0;
+  // joints of this thread in the DCN phase: the CTA's nj joints split over the two thread halves
+  const int jl_lo = half ? (nj + 1) / 2 : 0, jl_hi = half ? nj : (nj + 1) / 2;
+  const int msk_col0 = 18 * nj;
+
+  for (int g = blockIdx.x; g < B * tiles; g += gridDim.x) {
+    const int b = g / tiles, tile = g % tiles;
+    const int p = tile * kTM + tok;
+    const bool live = p < P;
+    const int h = live ? p / W : 0, w = live ? p % W : 0;
+    // ---- im2col: 9 dilated taps of the 32-channel feature, this thread's 16 channels ----
+    {
+      const float *tb = trans + ((size_t)b * kCin + half * 16) * P;
+#pragma unroll 3
+      for (int t = 0; t < kTaps; ++t) {
+        const int hh = h + (t / 3 - 1) * dil, ww = w + (t % 3 - 1) * dil;
+        const bool ok = live && hh >= 0 && hh < H && ww >= 0 && ww < W;
+        const float *src = tb + (ok ? hh * W + ww : 0);
+        float v[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = ok ? __ldg(src + (size_t)c * P) : 0.f;
+        uint8_t *dst = as + t * kATap + cm_offset(tok, half * 16, kRS32, kCS);
+        *reinterpret_cast<uint4 *>(dst) = pack16x8<F16>(v);
+        *reinterpret_cast<uint4 *>(dst + kCS) = pack16x8<F16>(v + 8);
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      const uint32_t a0 = smem_u32(as), w0 = smem_u32(ws);
+#pragma unroll
+      for (int t = 0; t < kTaps; ++t)
+#pragma unroll
+        for (int s = 0; s < kCin / 16; ++s)
+          umma_bf16(tm, make_desc(a0 + t * kATap + s * 2 * kCS, kCS, kRS32),
+                    make_desc(w0 + t * kWTap + s * 2 * kCS, kCS, kRS32), idesc, (t > 0 || s > 0));
+      umma_commit(&bar);
+    }
+    mbar_wait(&bar, ph);
+    ph ^= 1;
+    tc_fence_after();
+    // ---- modulated deformable sampling + 17 x (nj*9) contraction, offsets/masks from TMEM ----
+    float acc[kJ];
+#pragma unroll
+    for (int o = 0; o < kJ; ++o) acc[o] = 0.f;
+    const uint32_t trow = tm + ((uint32_t)(q4 * 32) << 16);
+    const float *xb = x + (size_t)b * kJ * P;
+#pragma unroll 1
+    for (int jl = jl_lo; jl < jl_hi; ++jl) {
+      float off[18], msk[9];
+      {
+        float t16[16];
+        tmem_ldn(trow + 18 * jl, t16);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) off[i] = t16[i];
+        tmem_ld2(trow + 18 * jl + 16, off[16], off[17]);
+        float m8[8];
+        tmem_ld8(trow + msk_col0 + 9 * jl, m8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) msk[i] = m8[i];
+        tmem_ld1(trow + msk_col0 + 9 * jl + 8, msk[8]);
+      }
+      if (live) {
+        const float *img = xb + (size_t)(j0 + jl) * P;
+#pragma unroll
+        for (int t = 0; t < kTaps; ++t) {
+          const float h_im = (float)(h + (t / 3 - 1) * dil) + off[2 * t];
+          const float w_im = (float)(w + (t % 3 - 1) * dil) + off[2 * t + 1];
+          float val = 0.f;
+          if (h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W) {
+            const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+            const int h_high = h_low + 1, w_high = w_low + 1;
+            const float lh = h_im - (float)h_low, lw = w_im - (float)w_low;
+            const float hh = 1.f - lh, hw = 1.f - lw;
+            float v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f;
+            if (h_low >= 0 && w_low >= 0) v1 = __ldg(img + h_low * W + w_low);
+            if (h_low >= 0 && w_high <= W - 1) v2 = __ldg(img + h_low * W + w_high);
+            if (h_high <= H - 1 && w_low >= 0) v3 = __ldg(img + h_high * W + w_low);
+            if (h_high <= H - 1 && w_high <= W - 1) v4 = __ldg(img + h_high * W + w_high);
+            val = (hh * hw) * v1 + (hh * lw) * v2 + (lh * hw) * v3 + (lh * lw) * v4;
+          }
+          const float col = val * msk[t];
+          const float *wr = wd + jl * 9 + t;
+#pragma unroll
+          for (int o = 0; o < kJ; ++o) acc[o] = fmaf(wr[o * 81], col, acc[o]);
+        }
+      }
+    }
+    // ---- combine the two thread halves (exchange buffer aliases the dead im2col taps) ----
+    float *ex = reinterpret_cast<float *>(as);
+    if (half == 1) {
+#pragma unroll
+      for (int o = 0; o < kJ; ++o) ex[o * kTM + tok] = acc[o];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (half == 0 && live) {
+#pragma unroll
+      for (int o = 0; o < kJ; ++o) {
+        float v = acc[o] + ex[o * kTM + tok] + (dcn_b ? __ldg(dcn_b + o) : 0.f);
+        float *dst = out + ((size_t)b * kJ + o) * P + p;
+        *dst = accumulate ? fmaf(alpha, v, *dst) : alpha * v;
+      }
+    }
+    __syncthreads();   // exchange buffer / TMEM are rewritten by the next tile
+    tc_fence_after();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tm, 256);
+}
+
+// image row r of joint-half hf: offsets of its joints (18 each), then their masks (9 each)
+template <bool F16>
+__global__ void pack_offset_mask_kernel(const float *__restrict__ w_off, const float *__restrict__ w_msk,
+                                        uint8_t *__restrict__ dst, int j0, int nj) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= kTaps * kNPad * kCin) return;
+  const int c = e % kCin, r = (e / kCin) % kNPad, t = e / (kCin * kNPad);
+  float v = 0.f;
+  if (r < 18 * nj) v = w_off[((size_t)(j0 * 18 + r) * kCin + c) * 9 + t];
+  else if (r < 27 * nj) v = w_msk[((size_t)(j0 * 9 + r - 18 * nj) * kCin + c) * 9 + t];
+  *reinterpret_cast<unsigned short *>(dst + (size_t)t * kWTap + cm_offset(r, c, kRS32, kCS)) = to16<F16>(v);
+}
+
+}  // namespace
+}  // namespace otp
+
+using namespace otp;
+
+extern "C" size_t otp_offset_mask_pack_bytes(void) { return kPackBytes; }
+
+extern "C" int otp_offset_mask_pack(const float *w_off, const float *w_msk, int joints, int cin, void *packed,
+                                    size_t packed_bytes, otp_stream_t stream) {
+  if (joints != kJ || cin != kCin) {
+    set_error("fused offset/mask/DCN kernel is built for 17 joints x 32 channels (got %d x %d)", joints, cin);
+    return OTP_ERR_UNSUPPORTED;
+  }
+  OTP_REQUIRE(w_off && w_msk && packed);
+  if (packed_bytes < kPackBytes) {
+    set_error("otp_offset_mask_pack: buffer of %zu B, need %zu B", packed_bytes, kPackBytes);
+    return OTP_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  LaunchScope ls(K_PACK, st, 4);
+  const int n = kTaps * kNPad * kCin;
+  for (int hf = 0; hf < 2; ++hf) {
+    uint8_t *d = static_cast<uint8_t *>(packed);
+    pack_offset_mask_kernel<false><<<ceil_div(n, 256), 256, 0, st>>>(w_off, w_msk, d + (0 * 2 + hf) * (size_t)kWSlice,
+                                                                      kJ0[hf], kNJ[hf]);
+    pack_offset_mask_kernel<true><<<ceil_div(n, 256), 256, 0, st>>>(w_off, w_msk, d + (1 * 2 + hf) * (size_t)kWSlice,
+                                                                     kJ0[hf], kNJ[hf]);
+  }
+  return check_launch("pack_offset_mask_kernel");
+}
+
+extern "C" int otp_offset_mask_dcn_forward(const void *packed, const float *trans, const float *x,
+                                           const float *dcn_w, const float *dcn_b, float *out, int b, int h,
+                                           int w, int dilation, float alpha, int accumulate, int precision,
+                                           otp_stream_t stream) {
+  OTP_REQUIRE(b >= 0 && h > 0 && w > 0 && dilation > 0);
+  OTP_REQUIRE(precision == OTP_PREC_BF16 || precision == OTP_PREC_FP16);
+  if (b == 0) return OTP_OK;
+  OTP_REQUIRE(packed && trans && x && dcn_w && out);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool f16 = precision == OTP_PREC_FP16;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(tc_dcn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+    cudaFuncSetAttribute(tc_dcn_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+    attr_done = true;
+  }
+  const int tiles = ceil_div(h * w, kTM);
+  const int grid = b * tiles < num_sms() ? b * tiles : num_sms();
+  for (int hf = 0; hf < 2; ++hf) {
+    const uint8_t *wimg = static_cast<const uint8_t *>(packed) + ((f16 ? 2 : 0) + hf) * (size_t)kWSlice;
+    LaunchScope ls(K_TC_CONV, st);
+    if (f16)
+      tc_dcn_fused_kernel<true><<<grid, kThreads, kSmem, st>>>(wimg, trans, x, dcn_w, hf == 0 ? dcn_b : nullptr, out,
+                                                              b, h, w, dilation, kJ0[hf], kNJ[hf], alpha,
+                                                              hf == 0 ? accumulate : 1, tiles);
+    else
+      tc_dcn_fused_kernel<false><<<grid, kThreads, kSmem, st>>>(wimg, trans, x, dcn_w, hf == 0 ? dcn_b : nullptr,
+                                                               out, b, h, w, dilation, kJ0[hf], kNJ[hf], alpha,
+                                                               hf == 0 ? accumulate : 1, tiles);
+  }
+  return check_launch("tc_dcn_fused_kernel");
+}

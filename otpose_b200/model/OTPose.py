@@ -133,6 +133,22 @@ class OTPose(nn.Module):
                     if m.bias is not None:
                         m.bias.zero_()
 
+    def _offset_mask_packed(self, i):
+        """16-bit operand images of offsets_list[i] / masks_list[i] for the fused tensor-core
+        kernel; rebuilt when either weight changed."""
+        wo, wm = self.offsets_list[i][0].weight, self.masks_list[i][0].weight
+        key = (wo.data_ptr(), wo._version, wm.data_ptr(), wm._version)
+        cache = self.__dict__.setdefault("_om_cache", {})
+        if cache.get(i, (None, None))[0] != key:
+            lib = _lib.load()
+            buf = torch.empty(lib.otp_offset_mask_pack_bytes(), dtype=torch.uint8, device=wo.device)
+            with torch.cuda.device(wo.device):
+                _lib.check(lib.otp_offset_mask_pack(_lib.dptr(wo.detach()), _lib.dptr(wm.detach()), self.num_joints,
+                                                    wo.shape[1], buf.data_ptr(), buf.numel(),
+                                                    _lib.stream_ptr(wo.device)), "otp_offset_mask_pack")
+            cache[i] = (key, buf)
+        return cache[i][1]
+
     # ------------------------------------------------------------------
     def forward(self, x, **kwargs):
         """Reference signature: x (B, 15, Himg, Wimg), margin=(B, 4)."""
@@ -202,19 +218,32 @@ class OTPose(nn.Module):
             if _debug is not None:
                 _debug.update(cat=cat, trans=trans, def_heatmaps=def_heatmaps)
             cdef = trans.shape[1]
-            k2 = 9
-            offsets = torch.empty((b, 2 * k2 * j, h, w), **f32)
-            masks = torch.empty((b, k2 * j, h, w), **f32)
             ww = 1.0 / len(self.deformable_conv_dilations)
-            for i, dd in enumerate(self.deformable_conv_dilations):
-                for conv, dst in ((self.offsets_list[i][0], offsets), (self.masks_list[i][0], masks)):
-                    _lib.check(lib.otp_conv2d(
-                        _lib.dptr(trans), cdef * t, None, 0, _lib.dptr(conv.weight.detach()), None, None, 0,
-                        dst.data_ptr(), dst.shape[1] * t, b, cdef, h, w, dst.shape[1], 3, dd, 0, st), "otp_conv2d")
-                dcn = self.modulated_deform_conv_list[i].deform_conv
+            prec = _lib.precision_code(self.precision)
+            fused = prec != _lib.PREC_FP32 and j == 17 and cdef == 32
+            if fused:
+                # offsets / masks never reach HBM: implicit-GEMM conv on tcgen05 feeding the DCN from TMEM
+                for i, dd in enumerate(self.deformable_conv_dilations):
+                    dcn = self.modulated_deform_conv_list[i].deform_conv
+                    _lib.check(lib.otp_offset_mask_dcn_forward(
+                        self._offset_mask_packed(i).data_ptr(), _lib.dptr(trans), _lib.dptr(def_heatmaps),
+                        _lib.dptr(dcn.weight.detach()), _lib.dptr(dcn.bias.detach() if dcn.bias is not None else None,
+                                                                  allow_none=True),
+                        out.data_ptr(), b, h, w, dd, ww, int(i > 0), prec, st), "otp_offset_mask_dcn_forward")
+            else:
                 from ..thirdparty.deform_conv import modulated_deform_conv
-                modulated_deform_conv(def_heatmaps, offsets, masks, dcn.weight, dcn.bias, dcn.stride,
-                                      dcn.padding, dcn.dilation, dcn.groups, dcn.deformable_groups,
-                                      alpha=ww, out=out, accumulate=(i > 0))
+                k2 = 9
+                offsets = torch.empty((b, 2 * k2 * j, h, w), **f32)
+                masks = torch.empty((b, k2 * j, h, w), **f32)
+                for i, dd in enumerate(self.deformable_conv_dilations):
+                    for conv, dst in ((self.offsets_list[i][0], offsets), (self.masks_list[i][0], masks)):
+                        _lib.check(lib.otp_conv2d(
+                            _lib.dptr(trans), cdef * t, None, 0, _lib.dptr(conv.weight.detach()), None, None, 0,
+                            dst.data_ptr(), dst.shape[1] * t, b, cdef, h, w, dst.shape[1], 3, dd, 0, st),
+                            "otp_conv2d")
+                    dcn = self.modulated_deform_conv_list[i].deform_conv
+                    modulated_deform_conv(def_heatmaps, offsets, masks, dcn.weight, dcn.bias, dcn.stride,
+                                          dcn.padding, dcn.dilation, dcn.groups, dcn.deformable_groups,
+                                          alpha=ww, out=out, accumulate=(i > 0))
         return (out, rough_heatmaps, intersection, prev_b, ctx.view(b, j, h, w),
                 squeezed.expand(b, j, h, w), total_b)

@@ -168,6 +168,40 @@ def test_mdcn_full_size_vs_torchvision_and_linearity():
     assert rel(acc, 1.5 * out1) < 1e-6
 
 
+@pytest.mark.parametrize("fmt,tol", [("fp16", 3e-3), ("bf16", 2e-2)])
+@pytest.mark.parametrize("b,h,w,d", [(2, 96, 72, 3), (1, 96, 72, 15), (3, 13, 11, 6), (150, 16, 12, 9)])
+def test_fused_offset_mask_dcn_vs_unfused(b, h, w, d, fmt, tol):
+    """a8+a9+a10: tensor-core implicit-GEMM offset/mask conv feeding the DCN from TMEM vs
+    fp32 conv2d (ATen) + the fp32 DCN kernel + weighted accumulation."""
+    import torch.nn.functional as F
+    r = np.random.default_rng(d)
+    trans = cuda(np.maximum(r.standard_normal((b, 32, h, w)), 0).astype(np.float32))
+    x = cuda(r.standard_normal((b, 17, h, w)).astype(np.float32))
+    w_off = cuda((r.standard_normal((306, 32, 3, 3)) * 2 / np.sqrt(288)).astype(np.float32))
+    w_msk = cuda((r.standard_normal((153, 32, 3, 3)) / np.sqrt(288)).astype(np.float32))
+    dcn_w = cuda(r.standard_normal((17, 17, 3, 3)).astype(np.float32) / 12)
+    dcn_b = cuda(r.standard_normal(17).astype(np.float32))
+    off = F.conv2d(trans, w_off, padding=d, dilation=d)
+    msk = F.conv2d(trans, w_msk, padding=d, dilation=d)
+    prev = cuda(r.standard_normal((b, 17, h, w)).astype(np.float32))
+    ref = prev + 0.2 * modulated_deform_conv(x, off, msk, dcn_w, dcn_b, 1, d, d, 1, 17)
+    lib = _lib.load()
+    packed = torch.empty(lib.otp_offset_mask_pack_bytes(), dtype=torch.uint8, device="cuda")
+    _lib.check(lib.otp_offset_mask_pack(w_off.data_ptr(), w_msk.data_ptr(), 17, 32, packed.data_ptr(),
+                                        packed.numel(), None))
+    out = prev.clone()
+    _lib.check(lib.otp_offset_mask_dcn_forward(packed.data_ptr(), trans.data_ptr(), x.data_ptr(), dcn_w.data_ptr(),
+                                               dcn_b.data_ptr(), out.data_ptr(), b, h, w, d, 0.2, 1,
+                                               _lib.precision_code(fmt), None))
+    assert rel(out, ref) < tol
+    out2 = torch.empty_like(out)       # accumulate = 0 overwrites
+    _lib.check(lib.otp_offset_mask_dcn_forward(packed.data_ptr(), trans.data_ptr(), x.data_ptr(), dcn_w.data_ptr(),
+                                               None, out2.data_ptr(), b, h, w, d, 1.0, 0,
+                                               _lib.precision_code(fmt), None))
+    ref2 = modulated_deform_conv(x, off, msk, dcn_w, None, 1, d, d, 1, 17)
+    assert rel(out2, ref2) < tol
+
+
 # ----------------------------------------------------------------- a1 prologue
 def test_fusion_prologue_vs_oracle():
     b, j, h, w = 3, 17, 12, 8
