@@ -15,7 +15,9 @@ struct BlockCfg<136> {
 };
 template <>
 struct BlockCfg<17> {
-  static constexpr int C = 17, NH = 1, HS = 17, NPT = 2, NWARP = 9, NPAD = 18;
+  // 2 warps x 9 channels: the 17-wide blocks are latency / barrier bound, so small CTAs
+  // (many resident per SM) beat wide ones
+  static constexpr int C = 17, NH = 1, HS = 17, NPT = 9, NWARP = 2, NPAD = 18;
 };
 
 constexpr int kTT = 64;           // output tokens per tile
@@ -101,9 +103,15 @@ inline BlockWorkspace block_workspace(int b, int c, int t, int n_head, int strid
   BlockWorkspace w{};
   w.tout = stride == 1 ? t : (t - 1) / 2 + 1;
   const int tiles = ceil_div(w.tout, kTT);
-  w.tiles_per_chunk = (int)((((long long)tiles * b) + 295) / 296);
+  // front-pass CTAs: ~2 per SM for the wide (1 CTA/SM) C=136 kernel, many small ones for C=17
+  const long long target = c == 136 ? 296 : 4096;
+  w.tiles_per_chunk = (int)((((long long)tiles * b) + target - 1) / target);
   if (w.tiles_per_chunk < 1) w.tiles_per_chunk = 1;
   w.nchunk = ceil_div(tiles, w.tiles_per_chunk);
+  if (c == 17) {   // thread-per-token kernels (block_small.cu): one partial Gram per 128-token CTA
+    w.tiles_per_chunk = 1;
+    w.nchunk = ceil_div(w.tout, 128);
+  }
   const size_t hs = c / n_head, np = npad_of(c);
   size_t o = 0;
   auto take = [&](size_t bytes) {

@@ -22,6 +22,7 @@
 // This file is the CUDA-core fp32 implementation (exact-precision mode and the
 // C=17 flow encoder); block_tc.cu holds the tcgen05 version of the same passes.
 #include "block_common.cuh"
+#include "block_fold.cuh"
 
 namespace otp {
 
@@ -232,66 +233,6 @@ block_front_kernel(BlockPack P, const float *__restrict__ x, float *__restrict__
     for (int jj = 0; jj < JB; ++jj) {
       gp[jj] = g[0][jj];
       if (has_r1) gp[HS + jj] = g[1][jj];
-    }
-  }
-}
-
-// ------------------------------------------------------------------ softmax + fold
-constexpr int kFoldThreads = 256;
-constexpr int kFoldSplit = 4;
-
-template <int C_>
-__global__ void __launch_bounds__(kFoldThreads)
-block_fold_kernel(BlockPack P, const float *__restrict__ gram_part, int nchunk,
-                  float *__restrict__ weffT, float *__restrict__ beff) {
-  using Cfg = BlockCfg<C_>;
-  constexpr int C = Cfg::C, HS = Cfg::HS, NPAD = Cfg::NPAD, LDS = HS + 1;
-  __shared__ float S[C * LDS];
-  const int b = blockIdx.x, cs = blockIdx.y;
-  const float *gp = gram_part + (size_t)b * nchunk * C * HS;
-  for (int e = threadIdx.x; e < C * HS; e += kFoldThreads) {
-    float s = 0.f;
-    for (int ch = 0; ch < nchunk; ++ch) s += __ldg(gp + (size_t)ch * C * HS + e);  // fixed order
-    S[(e / HS) * LDS + e % HS] = s;
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int r = warp; r < C; r += kFoldThreads / 32) {
-    float *row = S + r * LDS;
-    float m = -3.402823466e38f;
-    for (int j = lane; j < HS; j += 32) m = fmaxf(m, row[j]);
-    m = warp_max(m);
-    float sum = 0.f;
-    for (int j = lane; j < HS; j += 32) {
-      float e = expf(row[j] - m);
-      row[j] = e;
-      sum += e;
-    }
-    sum = warp_sum(sum);
-    const float inv = 1.0f / sum;
-    for (int j = lane; j < HS; j += 32) row[j] *= inv;
-  }
-  __syncthreads();
-  const int c_lo = (C * cs) / kFoldSplit, c_hi = (C * (cs + 1)) / kFoldSplit;
-  for (int idx = threadIdx.x; idx < (c_hi - c_lo) * NPAD; idx += kFoldThreads) {
-    const int n = idx % NPAD, c = c_lo + idx / NPAD;
-    float acc = 0.f;
-    if (n < C) {
-      const int h = n / HS;
-      const float *a = S + n * LDS;
-      const float *wv = P.wv + (size_t)(h * HS) * C + c;
-      for (int j = 0; j < HS; ++j) acc = fmaf(a[j], __ldg(wv + (size_t)j * C), acc);
-    }
-    weffT[((size_t)b * C + c) * NPAD + n] = acc;
-  }
-  if (cs == 0) {
-    for (int n = threadIdx.x; n < NPAD; n += kFoldThreads) {
-      float acc = 0.f;
-      if (n < C) {
-        const int h = n / HS;
-        for (int j = 0; j < HS; ++j) acc = fmaf(S[n * LDS + j], __ldg(P.bv + h * HS + j), acc);
-      }
-      beff[(size_t)b * NPAD + n] = acc;
     }
   }
 }
@@ -535,7 +476,8 @@ static int block_forward_simt_t(const void *packed, const float *x, float *y, in
   }
   {
     LaunchScope ls(K_BLOCK_FOLD, st);
-    block_fold_kernel<C_><<<dim3(b, kFoldSplit), kFoldThreads, 0, st>>>(P, gram, W.nchunk, weffT, beff);
+    block_fold_kernel<C_, 0><<<dim3(b, FoldCfg<C_>::NBLK), kFoldThreads, 0, st>>>(P.wv, P.bv, gram, W.nchunk, weffT,
+                                                                                 beff, C, Cfg::NPAD);
   }
   {
     LaunchScope ls(K_BLOCK_APPLY, st);
@@ -549,10 +491,13 @@ static int block_forward_simt_t(const void *packed, const float *x, float *y, in
   return check_launch("block_forward_simt");
 }
 
+int block_forward_small(const void *packed, const float *x, float *y, int b, int t, int stride, void *ws,
+                        cudaStream_t st);   // block_small.cu: thread-per-token kernels for C = 17
+
 int block_forward_simt(const void *packed, const float *x, float *y, int b, int c, int t, int stride,
                        void *ws, cudaStream_t st) {
   if (c == 136) return block_forward_simt_t<136>(packed, x, y, b, t, stride, ws, st);
-  return block_forward_simt_t<17>(packed, x, y, b, t, stride, ws, st);
+  return block_forward_small(packed, x, y, b, t, stride, ws, st);
 }
 
 }  // namespace otp

@@ -9,18 +9,26 @@
 //             tiles re-read as MN-major operands, accumulated in TMEM over the CTA's
 //             whole token chunk                                                 (tensor)
 //             vn (16-bit, already in operand layout) is written for tc_apply.
-//   fold      softmax + W_eff = softmax(S) W_v, emitted as an operand image.
+//   fold      softmax + W_eff = softmax(S) W_v, emitted as an operand image (block_fold.cuh).
 //   tc_apply  o = W_eff vn + b_eff : one M128 x N144 x K144 UMMA per tile, stored
 //             token-major 16-bit == the reference's scramble buffer.
 //   tc_back   proj UMMA -> u = skip + s_a(.) -> LN2 (registers) -> 6 x { W1 chunk UMMA
-//             (N96) -> bias + erf-GELU -> H tile -> W2 chunk UMMA accumulating in TMEM }
-//             -> y = u + s_m(.)
+//             (N96, double-buffered in TMEM so chunk j+1 runs under chunk j's GELU) ->
+//             bias + GELU -> H tile -> W2 chunk UMMA accumulating in TMEM } -> y = u + s_m(.)
 //
-// fp32 is kept for the residual stream, all LayerNorm statistics, the Gram
-// accumulation, softmax and every epilogue; only UMMA operands are 16-bit
-// (template F16: false = bfloat16, true = IEEE half -- same speed, 8x finer rounding;
-// every operand here is O(1)..O(100), far inside the half range).
+// fp32 is kept for the residual stream, all LayerNorm statistics, the Gram accumulation,
+// softmax and every epilogue; only UMMA operands are 16-bit (template F16: false =
+// bfloat16, true = IEEE half -- same speed, 8x finer rounding; every operand here is
+// O(1)..O(100), far inside the half range).  The affine part of LN_q/LN_k/LN_v/LN2 is
+// folded into the following GEMM's weights and bias when the weights are packed, so the
+// staged operands are plain (x - mean) * rstd.
+//
+// Thread map of the 384-thread CTAs: warp w -> TMEM lane quarter q4 = w % 4 (a hardware
+// rule of tcgen05.ld), token = 32*q4 + lane, and channel third = w / 4 (48 channels =
+// six 16-byte operand chunks), so a thread's registers, its LayerNorm partial sums and
+// its TMEM columns all refer to the same (token, channel-third).
 #include "block_common.cuh"
+#include "block_fold.cuh"
 #include "tc_common.cuh"
 
 namespace otp {
@@ -29,7 +37,8 @@ using namespace tc;
 namespace {
 constexpr int kC = 136, kHS = 68, kKP = 144;
 constexpr int kTM = 128;        // tokens per tile == UMMA M
-constexpr int kTcThreads = 256; // thread (q4, lane, half): token = 32*q4+lane, channel half
+constexpr int kTcThreads = 384;
+constexpr int kApplyThreads = 256;
 constexpr uint32_t kCS = 128;                 // byte stride between 8-element K chunks
 constexpr uint32_t kRS144 = (kKP / 8) * 128;  // byte stride between 8-row groups, K = 144
 constexpr uint32_t kTile144 = (kTM / 8) * kRS144;  // 36864  [128][144]
@@ -38,7 +47,6 @@ constexpr int kNH = 96, kNChunk = 6, kHidPad = kNH * kNChunk;  // hidden 544 -> 
 constexpr uint32_t kRS96 = (kNH / 8) * 128;        // 1536
 constexpr uint32_t kW1c = (kNH / 8) * kRS144;      // 27648  [96][144]
 constexpr uint32_t kW2c = (kKP / 8) * kRS96;       // 27648  [144][96]
-constexpr uint32_t kWc = kW1c + kW2c;              // 55296
 constexpr uint32_t kHTile = (kTM / 8) * kRS96;     // 24576  [128][96]
 constexpr int kXLD = 140;   // fp32 staging row stride; 136 staged tokens [s*ob-4, s*ob+132)
 constexpr int kXOff = 3;    // staged index of input token s*ob-1 (first tap of output token ob)
@@ -46,18 +54,23 @@ constexpr int kNI = 130;    // tokens the tile's taps touch
 
 // ---- packed tensor-core weights of one block (bytes) ----
 struct TcPack {
-  size_t wq, wk, wp, wc /* [6] x {W1 chunk, W2 chunk} */, img_bytes /* one operand format */;
-  size_t b1f /* fp32 [576], after both formats */, total;
+  size_t wq, wk, wp, w1 /* [6] */, w2 /* [6] */, img_bytes /* one operand format */;
+  size_t wvp /* fp32 [136][136] Wv * g_v */, bvp /* [144] */, bqp, bkp /* [144] */, b1p /* [576] */, total;
 };
 constexpr TcPack tc_pack_layout() {
   TcPack p{};
   p.wq = 0;
   p.wk = p.wq + kW144;
   p.wp = p.wk + kW144;
-  p.wc = p.wp + kW144;
-  p.img_bytes = p.wc + (size_t)kNChunk * kWc;
-  p.b1f = 2 * p.img_bytes;  // images: [bf16 set][fp16 set]
-  p.total = p.b1f + kHidPad * 4;
+  p.w1 = p.wp + kW144;
+  p.w2 = p.w1 + (size_t)kNChunk * kW1c;
+  p.img_bytes = p.w2 + (size_t)kNChunk * kW2c;
+  p.wvp = 2 * p.img_bytes;  // images: [bf16 set][fp16 set], then the fp32 folded vectors
+  p.bvp = p.wvp + (size_t)kC * kC * 4;
+  p.bqp = p.bvp + kKP * 4;
+  p.bkp = p.bqp + kKP * 4;
+  p.b1p = p.bkp + kKP * 4;
+  p.total = p.b1p + kHidPad * 4;
   return p;
 }
 
@@ -87,61 +100,120 @@ TcWorkspace tc_workspace(int b, int t, int stride) {
   return w;
 }
 
-// erf-GELU with the Abramowitz-Stegun 7.1.26 rational/exponential form
-// (|erf error| <= 1.5e-7): 1 MUFU.RCP + 1 MUFU.EX2 + ~12 FMA-pipe ops.
-__device__ __forceinline__ float gelu_as(float x) {
-  const float z = x * 0.70710678118654752440f;
-  const float az = fabsf(z);
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, az, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = __expf(-az * az);
-  const float erf_abs = fmaf(-p * t, e, 1.0f);
-  const float erf_z = copysignf(erf_abs, z);
-  return 0.5f * x * (1.0f + erf_z);
+// GELU of two pre-activations, returned as a packed 16-bit operand pair.
+// tanh form 0.5 x (1 + tanh(x (a + b x^2))) with (a, b) refitted to the erf GELU the
+// reference uses (nn.GELU default): max |error| 2.7e-4, below the half spacing of the
+// O(1) outputs it is rounded to.  F16: evaluated in packed half2 (7 instructions + one
+// MUFU per PAIR); bf16: fp32 arithmetic, rounded at the end.
+template <bool F16>
+__device__ __forceinline__ uint32_t gelu_pair(float a, float b) {
+  constexpr float kA = 0.80015708f, kB = 0.03470089f;
+  if constexpr (F16) {
+    const __half2 x = __floats2half2_rn(a, b);
+    const __half2 x2 = __hmul2(x, x);
+    const __half2 p = __hfma2(x2, __float2half2_rn(kB), __float2half2_rn(kA));
+    const __half2 t = h2tanh_approx(__hmul2(x, p));
+    const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
+    const __half2 o = __hfma2(hx, t, hx);
+    return *reinterpret_cast<const uint32_t *>(&o);
+  } else {
+    float r[2] = {a, b};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float x = r[i];
+      float t;
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * fmaf(kB, x * x, kA)));
+      r[i] = fmaf(0.5f * x, t, 0.5f * x);
+    }
+    return pack16x2<false>(r[0], r[1]);
+  }
 }
 
-// all threads: copy `bytes` (multiple of 16) global -> shared with cp.async
-__device__ __forceinline__ void cp_async_block(uint8_t *dst, const uint8_t *src, uint32_t bytes) {
-  for (uint32_t o = threadIdx.x * 16; o < bytes; o += kTcThreads * 16) cp_async16(dst + o, src + o);
+__device__ __forceinline__ void cp_async_block(uint8_t *dst, const uint8_t *src, uint32_t bytes, int nthreads) {
+  for (uint32_t o = threadIdx.x * 16; o < bytes; o += nthreads * 16) cp_async16(dst + o, src + o);
 }
 __device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
 }
 
+// tcgen05.ld without the wait, plus a wait that the loaded registers depend on.
+__device__ __forceinline__ void tmem_ld16_nw(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void reg_fence16(uint32_t (&r)[16]) {   // orders uses of r[] after the wait above
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+               "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
+               "+r"(r[15])::"memory");
+}
+// 48 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld48(uint32_t taddr, float (&v)[48]) {
+  uint32_t r0[16], r1[16], r2[16];
+  tmem_ld16_nw(taddr, r0);
+  tmem_ld16_nw(taddr + 16, r1);
+  tmem_ld16_nw(taddr + 32, r2);
+  tmem_wait_ld();
+  reg_fence16(r0);
+  reg_fence16(r1);
+  reg_fence16(r2);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    v[i] = __uint_as_float(r0[i]);
+    v[16 + i] = __uint_as_float(r1[i]);
+    v[32 + i] = __uint_as_float(r2[i]);
+  }
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r0[16], r1[16];
+  tmem_ld16_nw(taddr, r0);
+  tmem_ld16_nw(taddr + 16, r1);
+  tmem_wait_ld();
+  reg_fence16(r0);
+  reg_fence16(r1);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    v[i] = __uint_as_float(r0[i]);
+    v[16 + i] = __uint_as_float(r1[i]);
+  }
+}
+
 struct TcIds {
-  int q4, lane, half, tok, warp;
+  int q4, lane, third, tok, warp;
 };
 __device__ __forceinline__ TcIds tc_ids() {
   TcIds t;
   t.warp = threadIdx.x >> 5;
   t.lane = threadIdx.x & 31;
   t.q4 = t.warp & 3;
-  t.half = t.warp >> 2;
+  t.third = t.warp >> 2;
   t.tok = t.q4 * 32 + t.lane;
   return t;
 }
 // TMEM address of (this thread's lane quarter, column col)
-__device__ __forceinline__ uint32_t tcol(uint32_t base, const TcIds &id, int col) {
-  return base + ((uint32_t)(id.q4 * 32) << 16) + (uint32_t)col;
+__device__ __forceinline__ uint32_t tcol(uint32_t base, int q4, int col) {
+  return base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)col;
 }
 
 // ------------------------------------------------------------------ tc_front
 struct FrontVec {  // small fp32 parameters staged in shared memory
   float ln1w[kC], ln1b[kC];
-  float4 dwq[kC], dwk[kC], dwv[kC];
-  float qnw[kC], qnb[kC], knw[kC], knb[kC], vnw[kC], vnb[kC];
-  float bq[kKP], bk[kKP];
-  float part[6][2][kTM];
+  float4 dw[3][kC];          // depthwise taps of q, k, v
+  float bq[kKP], bk[kKP];    // folded biases
+  float part[2][3][kTM];     // per-third partial (sum, sum of squares) per token
+  float parte[2][3][2];      // same for the two halo tokens 128, 129
 };
 
 template <bool F16>
 __global__ void __launch_bounds__(kTcThreads, 1)
-tc_front_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__restrict__ x,
-                float *__restrict__ gram_part, uint8_t *__restrict__ vn_img, int T, int Tout, int stride,
-                int tiles, int tiles_per_chunk, int nchunk, float qscale) {
+tc_front_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__restrict__ bqp,
+                const float *__restrict__ bkp, const float *__restrict__ x, float *__restrict__ gram_part,
+                uint8_t *__restrict__ vn_img, int T, int Tout, int stride, int tiles, int tiles_per_chunk,
+                int nchunk, float qscale) {
   extern __shared__ __align__(1024) uint8_t smem[];
   float *xs = reinterpret_cast<float *>(smem);  // [136][140] fp32 staging, later the Wk image
   uint8_t *aq = smem + kC * kXLD * 4;
@@ -155,19 +227,18 @@ tc_front_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__res
   const int b = blockIdx.y, chunk = blockIdx.x;
   constexpr TcPack L = tc_pack_layout();
 
-  cp_async_block(wq, tcw + L.wq, kW144);
+  cp_async_block(wq, tcw + L.wq, kW144, kTcThreads);
   cp_async_commit();
   for (int c = threadIdx.x; c < kC; c += kTcThreads) {
-    V->ln1w[c] = P.ln1_w[c]; V->ln1b[c] = P.ln1_b[c];
-    V->dwq[c] = make_float4(P.dwq[3 * c], P.dwq[3 * c + 1], P.dwq[3 * c + 2], 0.f);
-    V->dwk[c] = make_float4(P.dwk[3 * c], P.dwk[3 * c + 1], P.dwk[3 * c + 2], 0.f);
-    V->dwv[c] = make_float4(P.dwv[3 * c], P.dwv[3 * c + 1], P.dwv[3 * c + 2], 0.f);
-    V->qnw[c] = P.qn_w[c]; V->qnb[c] = P.qn_b[c]; V->knw[c] = P.kn_w[c]; V->knb[c] = P.kn_b[c];
-    V->vnw[c] = P.vn_w[c]; V->vnb[c] = P.vn_b[c];
+    V->ln1w[c] = P.ln1_w[c];
+    V->ln1b[c] = P.ln1_b[c];
+    V->dw[0][c] = make_float4(P.dwq[3 * c], P.dwq[3 * c + 1], P.dwq[3 * c + 2], 0.f);
+    V->dw[1][c] = make_float4(P.dwk[3 * c], P.dwk[3 * c + 1], P.dwk[3 * c + 2], 0.f);
+    V->dw[2][c] = make_float4(P.dwv[3 * c], P.dwv[3 * c + 1], P.dwv[3 * c + 2], 0.f);
   }
   for (int c = threadIdx.x; c < kKP; c += kTcThreads) {
-    V->bq[c] = P.bq[c];
-    V->bk[c] = P.bk[c];
+    V->bq[c] = bqp[c];
+    V->bk[c] = bkp[c];
   }
   if (threadIdx.x == 0) {
     mbar_init(&bar_mma, 1);
@@ -187,12 +258,12 @@ tc_front_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__res
   bool gram_pending = false;
 
   const float *xb = x + (size_t)b * kC * T;
-  const int c_lo = id.half * 72, c_hi = id.half ? kC : 72;
+  const int c_lo = id.third * 48, c_hi = min(kC, c_lo + 48);
   const int tile_begin = chunk * tiles_per_chunk;
   const int tile_end = min(tiles, tile_begin + tiles_per_chunk);
   const int ntok = kTM / stride;
   const bool vec_ok = (T & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-  const float *xsh = xs + kXOff;   // xsh[c*kXLD + i] = input token (s*ob - 1 + i)
+  float *xsh = xs + kXOff;   // xsh[c*kXLD + i] = input token (s*ob - 1 + i)
 
   for (int tile = tile_begin; tile < tile_end; ++tile) {
     const int t0 = tile * kTM;
@@ -222,122 +293,108 @@ tc_front_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__res
       cp_async_wait<0>();
       __syncthreads();
       // ---- LN1 over channels per staged token (two-pass, fp32) ----
-      const int extra = (id.tok < kNI - kTM) ? kTM + id.tok : -1;  // tokens 128, 129
+      const bool has_e = id.tok < kNI - kTM;   // this thread also covers halo token 128 + tok
+      const int extra = kTM + id.tok;
       {
         float s0 = 0.f, s1 = 0.f;
         for (int c = c_lo; c < c_hi; ++c) {
           s0 += xsh[c * kXLD + id.tok];
-          if (extra >= 0) s1 += xsh[c * kXLD + extra];
+          if (has_e) s1 += xsh[c * kXLD + extra];
         }
-        V->part[0][id.half][id.tok] = s0;
-        if (extra >= 0) V->part[1][id.half][id.tok] = s1;
+        V->part[0][id.third][id.tok] = s0;
+        if (has_e) V->parte[0][id.third][id.tok] = s1;
       }
       __syncthreads();
-      const float mu0 = (V->part[0][0][id.tok] + V->part[0][1][id.tok]) * (1.0f / kC);
-      const float mu1 = extra >= 0 ? (V->part[1][0][id.tok] + V->part[1][1][id.tok]) * (1.0f / kC) : 0.f;
+      const float mu0 = (V->part[0][0][id.tok] + V->part[0][1][id.tok] + V->part[0][2][id.tok]) * (1.0f / kC);
+      const float mu1 = has_e ? (V->parte[0][0][id.tok] + V->parte[0][1][id.tok] + V->parte[0][2][id.tok]) * (1.0f / kC)
+                              : 0.f;
       {
         float s0 = 0.f, s1 = 0.f;
         for (int c = c_lo; c < c_hi; ++c) {
-          float d = xsh[c * kXLD + id.tok] - mu0;
+          const float d = xsh[c * kXLD + id.tok] - mu0;
           s0 = fmaf(d, d, s0);
-          if (extra >= 0) {
-            float e = xsh[c * kXLD + extra] - mu1;
+          if (has_e) {
+            const float e = xsh[c * kXLD + extra] - mu1;
             s1 = fmaf(e, e, s1);
           }
         }
-        V->part[2][id.half][id.tok] = s0;
-        if (extra >= 0) V->part[3][id.half][id.tok] = s1;
+        V->part[1][id.third][id.tok] = s0;
+        if (has_e) V->parte[1][id.third][id.tok] = s1;
       }
       __syncthreads();
       {
-        const float r0 = 1.0f / sqrtf((V->part[2][0][id.tok] + V->part[2][1][id.tok]) * (1.0f / kC) + 1e-5f);
+        const float r0 = 1.0f / sqrtf((V->part[1][0][id.tok] + V->part[1][1][id.tok] + V->part[1][2][id.tok]) *
+                                          (1.0f / kC) + 1e-5f);
         const bool v0 = (ib + id.tok >= 0) && (ib + id.tok < T);
         float r1 = 0.f;
         bool v1 = false;
-        if (extra >= 0) {
-          r1 = 1.0f / sqrtf((V->part[3][0][id.tok] + V->part[3][1][id.tok]) * (1.0f / kC) + 1e-5f);
+        if (has_e) {
+          r1 = 1.0f / sqrtf((V->parte[1][0][id.tok] + V->parte[1][1][id.tok] + V->parte[1][2][id.tok]) * (1.0f / kC) +
+                            1e-5f);
           v1 = (ib + extra >= 0) && (ib + extra < T);
         }
-        float *xw = xs + kXOff;
         for (int c = c_lo; c < c_hi; ++c) {
           const float w = V->ln1w[c], bb = V->ln1b[c];
-          float *p0 = xw + c * kXLD + id.tok;
+          float *p0 = xsh + c * kXLD + id.tok;
           *p0 = v0 ? fmaf((*p0 - mu0) * r0, w, bb) : 0.f;   // zero == conv zero padding
-          if (extra >= 0) {
-            float *p1 = xw + c * kXLD + extra;
+          if (has_e) {
+            float *p1 = xsh + c * kXLD + extra;
             *p1 = v1 ? fmaf((*p1 - mu1) * r1, w, bb) : 0.f;
           }
         }
       }
       __syncthreads();
-      // ---- depthwise convs + LN_q / LN_k / LN_v statistics (one pass: sum, sum of squares) ----
+      // ---- q, k, v in turn: depthwise conv (kept in registers) -> statistics -> (d-mean)*rstd ----
       const bool active = id.tok < ntok;
       const int xi = stride * id.tok;
-      float st[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (active) {
-        for (int c = c_lo; c < c_hi; ++c) {
-          const float *xr = xsh + c * kXLD + xi;
-          const float y0 = xr[0], y1 = xr[1], y2 = xr[2];
-          const float4 a = V->dwq[c], bb = V->dwk[c], cc = V->dwv[c];
-          const float dq = fmaf(a.z, y2, fmaf(a.y, y1, a.x * y0));
-          const float dk = fmaf(bb.z, y2, fmaf(bb.y, y1, bb.x * y0));
-          const float dv = fmaf(cc.z, y2, fmaf(cc.y, y1, cc.x * y0));
-          st[0] += dq; st[1] = fmaf(dq, dq, st[1]);
-          st[2] += dk; st[3] = fmaf(dk, dk, st[3]);
-          st[4] += dv; st[5] = fmaf(dv, dv, st[5]);
-        }
-      }
+      const int row = round * ntok + id.tok;
+#pragma unroll 1
+      for (int m = 0; m < 3; ++m) {
+        float d[48];
+        float s = 0.f, ss = 0.f;
+        if (active) {
 #pragma unroll
-      for (int k = 0; k < 6; ++k) V->part[k][id.half][id.tok] = st[k];
-      __syncthreads();
-      float mean[3], rs[3];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const float s = V->part[2 * k][0][id.tok] + V->part[2 * k][1][id.tok];
-        const float ss = V->part[2 * k + 1][0][id.tok] + V->part[2 * k + 1][1][id.tok];
-        mean[k] = s * (1.0f / kC);
-        const float var = fmaxf(ss * (1.0f / kC) - mean[k] * mean[k], 0.f);
-        rs[k] = 1.0f / sqrtf(var + 1e-5f);
-      }
-      // the previous tile's Gram UMMAs still read aq/ak: wait before overwriting them
-      if (gram_pending) {
-        mbar_wait(&bar_gram, ph_gram);
-        ph_gram ^= 1;
-        gram_pending = false;
-      }
-      // ---- normalise, round to 16 bit, store operand tiles (16-byte, conflict-free) ----
-      if (active) {
-        const int row = round * ntok + id.tok;
-        const int ch_lo = id.half ? 9 : 0, ch_hi = id.half ? 18 : 9;
-        for (int ch = ch_lo; ch < ch_hi; ++ch) {
-          float q8[8], k8[8], v8[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int c = ch * 8 + e;
+          for (int i = 0; i < 48; ++i) {
+            const int c = c_lo + i;
+            float v = 0.f;
             if (c < kC) {
               const float *xr = xsh + c * kXLD + xi;
-              const float y0 = xr[0], y1 = xr[1], y2 = xr[2];
-              const float4 a = V->dwq[c], bb = V->dwk[c], cc = V->dwv[c];
-              const float dq = fmaf(a.z, y2, fmaf(a.y, y1, a.x * y0));
-              const float dk = fmaf(bb.z, y2, fmaf(bb.y, y1, bb.x * y0));
-              const float dv = fmaf(cc.z, y2, fmaf(cc.y, y1, cc.x * y0));
-              q8[e] = fmaf((dq - mean[0]) * rs[0], V->qnw[c], V->qnb[c]);
-              k8[e] = fmaf((dk - mean[1]) * rs[1], V->knw[c], V->knb[c]);
-              v8[e] = fmaf((dv - mean[2]) * rs[2], V->vnw[c], V->vnb[c]);
-            } else {
-              q8[e] = k8[e] = v8[e] = 0.f;
+              const float4 w = V->dw[m][c];
+              v = fmaf(w.z, xr[2], fmaf(w.y, xr[1], w.x * xr[0]));
             }
+            d[i] = v;
+            s += v;
+            ss = fmaf(v, v, ss);
           }
-          const uint32_t off = cm_offset(row, ch * 8, kRS144, kCS);
-          *reinterpret_cast<uint4 *>(aq + off) = pack16x8<F16>(q8);
-          *reinterpret_cast<uint4 *>(ak + off) = pack16x8<F16>(k8);
-          *reinterpret_cast<uint4 *>(vn_tile + off) = pack16x8<F16>(v8);
         }
+        V->part[0][id.third][id.tok] = s;
+        V->part[1][id.third][id.tok] = ss;
+        __syncthreads();
+        const float mean = (V->part[0][0][id.tok] + V->part[0][1][id.tok] + V->part[0][2][id.tok]) * (1.0f / kC);
+        const float var = fmaxf((V->part[1][0][id.tok] + V->part[1][1][id.tok] + V->part[1][2][id.tok]) * (1.0f / kC) -
+                                    mean * mean, 0.f);
+        const float rstd = 1.0f / sqrtf(var + 1e-5f);
+        // the previous tile's Gram UMMAs still read aq/ak: wait before overwriting them
+        if (m == 0 && gram_pending) {
+          mbar_wait(&bar_gram, ph_gram);
+          ph_gram ^= 1;
+          gram_pending = false;
+        }
+        if (active) {
+          uint8_t *dst = (m == 0 ? aq : (m == 1 ? ak : vn_tile)) + cm_offset(row, c_lo, kRS144, kCS);
+#pragma unroll
+          for (int g = 0; g < 6; ++g) {
+            float o8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o8[e] = (c_lo + g * 8 + e < kC) ? (d[g * 8 + e] - mean) * rstd : 0.f;
+            *reinterpret_cast<uint4 *>(dst + g * kCS) = pack16x8<F16>(o8);
+          }
+        }
+        __syncthreads();   // part[] is rewritten by the next matrix; xs by the next round / Wk
       }
-      __syncthreads();  // xs is re-staged by the next round / reused for Wk
     }
     // ---- Wk image -> the (now dead) staging region; q and k projections on the tensor cores ----
-    cp_async_block(reinterpret_cast<uint8_t *>(xs), tcw + L.wk, kW144);
+    cp_async_block(reinterpret_cast<uint8_t *>(xs), tcw + L.wk, kW144, kTcThreads);
     cp_async_commit();
     cp_async_wait<0>();
     fence_async_smem();
@@ -347,15 +404,13 @@ tc_front_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__res
       tc_fence_after();
       const uint32_t a_q = smem_u32(aq), a_k = smem_u32(ak), w_q = smem_u32(wq), w_k = smem_u32(xs);
 #pragma unroll
-      for (int s = 0; s < kKP / 16; ++s) {
+      for (int s = 0; s < kKP / 16; ++s)
         umma_bf16(t_q, make_desc(a_q + s * 2 * kCS, kCS, kRS144), make_desc(w_q + s * 2 * kCS, kCS, kRS144),
                   idesc_qk, s > 0);
-      }
 #pragma unroll
-      for (int s = 0; s < kKP / 16; ++s) {
+      for (int s = 0; s < kKP / 16; ++s)
         umma_bf16(t_k, make_desc(a_k + s * 2 * kCS, kCS, kRS144), make_desc(w_k + s * 2 * kCS, kCS, kRS144),
                   idesc_qk, s > 0);
-      }
       umma_commit(&bar_mma);
     }
     mbar_wait(&bar_mma, ph_mma);
@@ -364,20 +419,24 @@ tc_front_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__res
     // ---- epilogue: + bias, * 1/sqrt(hs) for q, 16 bit, back into aq / ak as [token][channel] ----
     {
       const bool live = id.tok < nvalid;   // padded tokens must not reach the Gram
-#pragma unroll 1
-      for (int g = 0; g < 9; ++g) {
-        const int col = id.half * 72 + g * 8;
-        float vq[8], vk[8];
-        tmem_ld8(tcol(t_q, id, col), vq);
-        tmem_ld8(tcol(t_k, id, col), vk);
+      const int col = id.third * 48;
+      const uint32_t off = cm_offset(id.tok, col, kRS144, kCS);
+      float v[48];
+      tmem_ld48(tcol(t_q, id.q4, col), v);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          vq[e] = live ? (vq[e] + V->bq[col + e]) * qscale : 0.f;
-          vk[e] = live ? (vk[e] + V->bk[col + e]) : 0.f;
-        }
-        const uint32_t off = cm_offset(id.tok, col, kRS144, kCS);
-        *reinterpret_cast<uint4 *>(aq + off) = pack16x8<F16>(vq);
-        *reinterpret_cast<uint4 *>(ak + off) = pack16x8<F16>(vk);
+      for (int g = 0; g < 6; ++g) {
+        float o8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o8[e] = live ? (v[g * 8 + e] + V->bq[col + g * 8 + e]) * qscale : 0.f;
+        *reinterpret_cast<uint4 *>(aq + off + g * kCS) = pack16x8<F16>(o8);
+      }
+      tmem_ld48(tcol(t_k, id.q4, col), v);
+#pragma unroll
+      for (int g = 0; g < 6; ++g) {
+        float o8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o8[e] = live ? v[g * 8 + e] + V->bk[col + g * 8 + e] : 0.f;
+        *reinterpret_cast<uint4 *>(ak + off + g * kCS) = pack16x8<F16>(o8);
       }
     }
     fence_async_smem();
@@ -408,16 +467,16 @@ tc_front_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__res
   }
   tc_fence_after();
   // ---- flush the partial Gram: TMEM lane == q channel (row), column == k channel ----
-  {
+  if (id.third < 2) {
     float *gp = gram_part + (size_t)(b * nchunk + chunk) * kC * kHS;
-    const int row_ch = id.half ? 8 + id.tok : id.tok;          // q channel of this lane
-    const bool row_ok = id.half ? (row_ch >= kHS && row_ch < kC) : (row_ch < kHS);
-    const int col0 = id.half ? 4 : 0;                            // first useful column
-    const uint32_t tg = id.half ? t_g1 : t_g0;
+    const int row_ch = id.third ? 8 + id.tok : id.tok;          // q channel of this lane
+    const bool row_ok = id.third ? (row_ch >= kHS && row_ch < kC) : (row_ch < kHS);
+    const int col0 = id.third ? 4 : 0;                            // first useful column
+    const uint32_t tg = id.third ? t_g1 : t_g0;
 #pragma unroll 1
     for (int g = 0; g < 10; ++g) {
       float v[8];
-      tmem_ld8(tcol(tg, id, g * 8), v);
+      tmem_ld8(tcol(tg, id.q4, g * 8), v);
       if (row_ok) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -432,67 +491,9 @@ tc_front_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__res
   if (id.warp == 0) tmem_dealloc(tm, 512);
 }
 
-// ------------------------------------------------------------------ fold (operand image)
-template <bool F16>
-__global__ void __launch_bounds__(256)
-tc_fold_kernel(BlockPack P, const float *__restrict__ gram_part, int nchunk, uint8_t *__restrict__ weff_img,
-               float *__restrict__ beff) {
-  constexpr int LDS = kHS + 1;
-  __shared__ float S[kC * LDS];
-  const int b = blockIdx.x, cs = blockIdx.y;
-  const float *gp = gram_part + (size_t)b * nchunk * kC * kHS;
-  for (int e = threadIdx.x; e < kC * kHS; e += 256) {
-    float s = 0.f;
-    for (int ch = 0; ch < nchunk; ++ch) s += __ldg(gp + (size_t)ch * kC * kHS + e);  // fixed order
-    S[(e / kHS) * LDS + e % kHS] = s;
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int r = warp; r < kC; r += 8) {
-    float *row = S + r * LDS;
-    float m = -3.402823466e38f;
-    for (int j = lane; j < kHS; j += 32) m = fmaxf(m, row[j]);
-    m = warp_max(m);
-    float sum = 0.f;
-    for (int j = lane; j < kHS; j += 32) {
-      float e = expf(row[j] - m);
-      row[j] = e;
-      sum += e;
-    }
-    sum = warp_sum(sum);
-    const float inv = 1.0f / sum;
-    for (int j = lane; j < kHS; j += 32) row[j] *= inv;
-  }
-  __syncthreads();
-  // W_eff[n][c] = sum_j A[n][j] * Wv[h(n)*hs + j][c]  -> image row n, K index c
-  uint8_t *img = weff_img + (size_t)b * kW144;
-  const int c_lo = (kKP * cs) / 4, c_hi = (kKP * (cs + 1)) / 4;
-  for (int idx = threadIdx.x; idx < (c_hi - c_lo) * kKP; idx += 256) {
-    const int n = idx % kKP, c = c_lo + idx / kKP;
-    float acc = 0.f;
-    if (n < kC && c < kC) {
-      const int h = n / kHS;
-      const float *a = S + n * LDS;
-      const float *wv = P.wv + (size_t)(h * kHS) * kC + c;
-      for (int j = 0; j < kHS; ++j) acc = fmaf(a[j], __ldg(wv + (size_t)j * kC), acc);
-    }
-    *reinterpret_cast<unsigned short *>(img + cm_offset(n, c, kRS144, kCS)) = to16<F16>(acc);
-  }
-  if (cs == 0) {
-    for (int n = threadIdx.x; n < kKP; n += 256) {
-      float acc = 0.f;
-      if (n < kC) {
-        const int h = n / kHS;
-        for (int j = 0; j < kHS; ++j) acc = fmaf(S[n * LDS + j], __ldg(P.bv + h * kHS + j), acc);
-      }
-      beff[(size_t)b * kKP + n] = acc;
-    }
-  }
-}
-
 // ------------------------------------------------------------------ tc_apply
 template <bool F16>
-__global__ void __launch_bounds__(kTcThreads, 2)
+__global__ void __launch_bounds__(kApplyThreads, 2)
 tc_apply_kernel(const uint8_t *__restrict__ vn_img, const uint8_t *__restrict__ weff_img,
                 const float *__restrict__ beff, unsigned short *__restrict__ obuf, int Tout, int tiles) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -501,18 +502,19 @@ tc_apply_kernel(const uint8_t *__restrict__ vn_img, const uint8_t *__restrict__ 
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
   __shared__ float sb[kKP];
-  const TcIds id = tc_ids();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q4 = warp & 3, half = warp >> 2;
+  const int tok = q4 * 32 + lane;
   const int b = blockIdx.y, tile = blockIdx.x;
   const int t0 = tile * kTM, nvalid = min(kTM, Tout - t0);
-  cp_async_block(a, vn_img + ((size_t)b * tiles + tile) * kTile144, kTile144);
-  cp_async_block(w, weff_img + (size_t)b * kW144, kW144);
+  cp_async_block(a, vn_img + ((size_t)b * tiles + tile) * kTile144, kTile144, kApplyThreads);
+  cp_async_block(w, weff_img + (size_t)b * kW144, kW144, kApplyThreads);
   cp_async_commit();
-  for (int n = threadIdx.x; n < kKP; n += kTcThreads) sb[n] = beff[(size_t)b * kKP + n];
+  for (int n = threadIdx.x; n < kKP; n += kApplyThreads) sb[n] = beff[(size_t)b * kKP + n];
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
     fence_mbar_init();
   }
-  if (id.warp == 0) tmem_alloc(&tmem_slot, 256);
+  if (warp == 0) tmem_alloc(&tmem_slot, 256);
   cp_async_wait<0>();
   fence_async_smem();
   tc_fence_before();
@@ -533,10 +535,10 @@ tc_apply_kernel(const uint8_t *__restrict__ vn_img, const uint8_t *__restrict__ 
   unsigned short *ob = obuf + (size_t)b * kC * Tout;
 #pragma unroll 1
   for (int g = 0; g < 9; ++g) {
-    const int col = id.half * 72 + g * 8;
+    const int col = half * 72 + g * 8;
     float v[8];
-    tmem_ld8(tcol(tm, id, col), v);
-    if (id.tok < nvalid) {
+    tmem_ld8(tcol(tm, q4, col), v);
+    if (tok < nvalid) {
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const int n4 = col + 4 * q;
@@ -545,48 +547,49 @@ tc_apply_kernel(const uint8_t *__restrict__ vn_img, const uint8_t *__restrict__ 
           uint2 pk;
           pk.x = pack16x2<F16>(v[4 * q] + sb[n4], v[4 * q + 1] + sb[n4 + 1]);
           pk.y = pack16x2<F16>(v[4 * q + 2] + sb[n4 + 2], v[4 * q + 3] + sb[n4 + 3]);
-          *reinterpret_cast<uint2 *>(ob + ((size_t)h * Tout + t0 + id.tok) * kHS + cp) = pk;
+          *reinterpret_cast<uint2 *>(ob + ((size_t)h * Tout + t0 + tok) * kHS + cp) = pk;
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (id.warp == 0) tmem_dealloc(tm, 256);
+  if (warp == 0) tmem_dealloc(tm, 256);
 }
 
 // ------------------------------------------------------------------ tc_back
 struct BackVec {
-  float bp[kKP], sa[kKP], b2[kKP], sm[kKP], ln2w[kKP], ln2b[kKP];
-  float b1f[kHidPad];
-  float part[2][2][kTM];
+  float bp[kKP], sa[kKP], b2[kKP], sm[kKP];
+  float b1p[kHidPad];
+  float part[2][3][kTM];
 };
 
 template <bool F16>
 __global__ void __launch_bounds__(kTcThreads, 1)
-tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__restrict__ b1f,
+tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__restrict__ b1p,
                const float *__restrict__ x, const unsigned short *__restrict__ obuf, float *__restrict__ y,
                int B, int T, int Tout, int stride, int tiles) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *a = smem;                    // out2 tile, then LN2(u)
   uint8_t *hbuf = a + kTile144;         // GELU(hidden chunk)
   uint8_t *wp = hbuf + kHTile;
-  uint8_t *wb0 = wp + kW144;
-  uint8_t *wb1 = wb0 + kWc;
-  BackVec *V = reinterpret_cast<BackVec *>(wb1 + kWc);
+  uint8_t *w1b = wp + kW144;            // 2 x W1 chunk
+  uint8_t *w2b = w1b + 2 * kW1c;        // 2 x W2 chunk
+  BackVec *V = reinterpret_cast<BackVec *>(w2b + 2 * kW2c);
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
   const TcIds id = tc_ids();
   constexpr TcPack L = tc_pack_layout();
 
-  cp_async_block(wp, tcw + L.wp, kW144);
+  cp_async_block(wp, tcw + L.wp, kW144, kTcThreads);
   cp_async_commit();
   for (int n = threadIdx.x; n < kKP; n += kTcThreads) {
-    V->bp[n] = P.bp[n]; V->sa[n] = P.sa[n]; V->b2[n] = P.b2[n]; V->sm[n] = P.sm[n];
-    V->ln2w[n] = n < kC ? P.ln2_w[n] : 0.f;
-    V->ln2b[n] = n < kC ? P.ln2_b[n] : 0.f;
+    V->bp[n] = P.bp[n];
+    V->sa[n] = P.sa[n];
+    V->b2[n] = P.b2[n];
+    V->sm[n] = P.sm[n];
   }
-  for (int n = threadIdx.x; n < kHidPad; n += kTcThreads) V->b1f[n] = b1f[n];
+  for (int n = threadIdx.x; n < kHidPad; n += kTcThreads) V->b1p[n] = b1p[n];
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
     fence_mbar_init();
@@ -596,49 +599,60 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__rest
   __syncthreads();
   tc_fence_after();
   const uint32_t tm = tmem_slot;
-  const uint32_t t_y = tm, t_a = tm + 144;   // y accumulator | proj accumulator, then hidden chunk
+  const uint32_t t_y = tm, t_p = tm + 144;           // y accumulator | proj accumulator (N = 144)
+  const uint32_t t_h[2] = {tm + 144, tm + 240};      // hidden chunk accumulators (N = 96), double-buffered
   constexpr uint32_t kFmt = F16 ? 0u : 1u;
   const uint32_t idesc144 = make_idesc_16(kKP, false, false, kFmt);
   const uint32_t idesc96 = make_idesc_16(kNH, false, false, kFmt);
   uint32_t ph = 0;
-  const int col_lo = id.half * 72;
+  const int col_lo = id.third * 48;
+
+  auto issue_mma1 = [&](int j) {   // hidden chunk j: D_h[j&1] = LN2(u) . W1_j^T
+    const uint32_t aa = smem_u32(a), w1 = smem_u32(w1b + (j & 1) * kW1c);
+#pragma unroll
+    for (int s = 0; s < kKP / 16; ++s)
+      umma_bf16(t_h[j & 1], make_desc(aa + s * 2 * kCS, kCS, kRS144), make_desc(w1 + s * 2 * kCS, kCS, kRS144),
+                idesc96, s > 0);
+  };
 
   for (int g = blockIdx.x; g < B * tiles; g += gridDim.x) {
     const int b = g / tiles, tile = g % tiles;
     const int t0 = tile * kTM, nvalid = min(kTM, Tout - t0);
     const bool live = id.tok < nvalid;
-    // weight chunks 0 and 1 in flight while the activations are staged
-    cp_async_block(wb0, tcw + L.wc, kWc);
+    // weight prologue: group A = {W1_0} (+ Wp on the first tile), group B = {W1_1, W2_0}
+    cp_async_block(w1b, tcw + L.w1, kW1c, kTcThreads);
     cp_async_commit();
-    cp_async_block(wb1, tcw + L.wc + kWc, kWc);
+    cp_async_block(w1b + kW1c, tcw + L.w1 + kW1c, kW1c, kTcThreads);
+    cp_async_block(w2b, tcw + L.w2, kW2c, kTcThreads);
     cp_async_commit();
     // ---- the (nh, T', hs) 16-bit buffer re-read as (C, T'): A tile [token][channel].
-    //      All 72 loads of a thread are issued before the first use (memory-level parallelism).
+    //      All loads of a thread are issued before the first use (memory-level parallelism).
     {
       const unsigned short *ob = obuf + (size_t)b * kC * Tout + t0 + id.tok;
-      unsigned short ov[72];
+      unsigned short ov[48];
 #pragma unroll
-      for (int i = 0; i < 72; ++i) {
+      for (int i = 0; i < 48; ++i) {
         const int c = col_lo + i;
         ov[i] = (live && c < kC) ? __ldg(ob + (size_t)c * Tout) : (unsigned short)0;
       }
+      uint8_t *dst = a + cm_offset(id.tok, col_lo, kRS144, kCS);
 #pragma unroll
-      for (int gg = 0; gg < 9; ++gg) {
+      for (int gg = 0; gg < 6; ++gg) {
         uint4 w4;
         w4.x = (uint32_t)ov[gg * 8 + 0] | ((uint32_t)ov[gg * 8 + 1] << 16);
         w4.y = (uint32_t)ov[gg * 8 + 2] | ((uint32_t)ov[gg * 8 + 3] << 16);
         w4.z = (uint32_t)ov[gg * 8 + 4] | ((uint32_t)ov[gg * 8 + 5] << 16);
         w4.w = (uint32_t)ov[gg * 8 + 6] | ((uint32_t)ov[gg * 8 + 7] << 16);
-        *reinterpret_cast<uint4 *>(a + cm_offset(id.tok, col_lo + gg * 8, kRS144, kCS)) = w4;
+        *reinterpret_cast<uint4 *>(dst + gg * kCS) = w4;
       }
     }
     // ---- skip path: pool_skip(x) prefetched into the registers that will hold u ----
-    float u[72];
+    float u[48];
     {
       const float *xb = x + (size_t)b * kC * T;
       const int tt = t0 + id.tok;
 #pragma unroll
-      for (int i = 0; i < 72; ++i) {
+      for (int i = 0; i < 48; ++i) {
         const int n = col_lo + i;
         float skip = 0.f;
         if (n < kC && live) {
@@ -655,7 +669,7 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__rest
         u[i] = skip;
       }
     }
-    cp_async_wait<2>();   // Wp (first tile); no-op afterwards
+    cp_async_wait<1>();   // group A (and Wp) landed
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -664,7 +678,7 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__rest
       const uint32_t aa = smem_u32(a), ww = smem_u32(wp);
 #pragma unroll
       for (int s = 0; s < kKP / 16; ++s)
-        umma_bf16(t_a, make_desc(aa + s * 2 * kCS, kCS, kRS144), make_desc(ww + s * 2 * kCS, kCS, kRS144), idesc144,
+        umma_bf16(t_p, make_desc(aa + s * 2 * kCS, kCS, kRS144), make_desc(ww + s * 2 * kCS, kCS, kRS144), idesc144,
                   s > 0);
       umma_commit(&bar);
     }
@@ -673,115 +687,110 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__rest
     tc_fence_after();
     // ---- u = skip(x) + s_a * (proj + b_p); LN2 statistics from registers ----
     {
+      float v[48];
+      tmem_ld48(tcol(t_p, id.q4, col_lo), v);
       float s = 0.f;
 #pragma unroll
-      for (int gg = 0; gg < 9; ++gg) {
-        float v[8];
-        tmem_ld8(tcol(t_a, id, col_lo + gg * 8), v);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int n = col_lo + gg * 8 + e;
-          const float val = (n < kC && live) ? fmaf(V->sa[n], v[e] + V->bp[n], u[gg * 8 + e]) : 0.f;
-          u[gg * 8 + e] = val;
-          s += val;
-        }
+      for (int i = 0; i < 48; ++i) {
+        const int n = col_lo + i;
+        const float val = (n < kC && live) ? fmaf(V->sa[n], v[i] + V->bp[n], u[i]) : 0.f;
+        u[i] = val;
+        s += val;
       }
-      V->part[0][id.half][id.tok] = s;
+      V->part[0][id.third][id.tok] = s;
     }
     __syncthreads();
-    const float mu = (V->part[0][0][id.tok] + V->part[0][1][id.tok]) * (1.0f / kC);
+    const float mu = (V->part[0][0][id.tok] + V->part[0][1][id.tok] + V->part[0][2][id.tok]) * (1.0f / kC);
     {
       float s = 0.f;
 #pragma unroll
-      for (int i = 0; i < 72; ++i) {
+      for (int i = 0; i < 48; ++i) {
         const float d = (col_lo + i < kC) ? u[i] - mu : 0.f;
         s = fmaf(d, d, s);
       }
-      V->part[1][id.half][id.tok] = s;
+      V->part[1][id.third][id.tok] = s;
     }
     __syncthreads();
     {
-      const float rstd = 1.0f / sqrtf((V->part[1][0][id.tok] + V->part[1][1][id.tok]) * (1.0f / kC) + 1e-5f);
+      const float rstd = 1.0f / sqrtf((V->part[1][0][id.tok] + V->part[1][1][id.tok] + V->part[1][2][id.tok]) *
+                                          (1.0f / kC) + 1e-5f);
+      uint8_t *dst = a + cm_offset(id.tok, col_lo, kRS144, kCS);
 #pragma unroll
-      for (int gg = 0; gg < 9; ++gg) {
+      for (int gg = 0; gg < 6; ++gg) {
         float h8[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int n = col_lo + gg * 8 + e;
-          h8[e] = fmaf((u[gg * 8 + e] - mu) * rstd, V->ln2w[n], V->ln2b[n]);   // pad channels: w = b = 0
-        }
-        *reinterpret_cast<uint4 *>(a + cm_offset(id.tok, col_lo + gg * 8, kRS144, kCS)) = pack16x8<F16>(h8);
+        for (int e = 0; e < 8; ++e) h8[e] = (col_lo + gg * 8 + e < kC) ? (u[gg * 8 + e] - mu) * rstd : 0.f;
+        *reinterpret_cast<uint4 *>(dst + gg * kCS) = pack16x8<F16>(h8);
       }
     }
-    // ---- MLP: hidden chunk j on the tensor cores, GELU on the CUDA cores, W2 accumulates in TMEM ----
-    cp_async_wait<1>();   // W chunk 0
+    // ---- MLP: W1 chunk j+1 runs on the tensor cores while the CUDA cores do GELU(chunk j) ----
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) {
       tc_fence_after();
-      const uint32_t aa = smem_u32(a), w1 = smem_u32(wb0);
-#pragma unroll
-      for (int s = 0; s < kKP / 16; ++s)
-        umma_bf16(t_a, make_desc(aa + s * 2 * kCS, kCS, kRS144), make_desc(w1 + s * 2 * kCS, kCS, kRS144), idesc96,
-                  s > 0);
+      issue_mma1(0);
       umma_commit(&bar);
     }
-    mbar_wait(&bar, ph);
-    ph ^= 1;
-    tc_fence_after();
 #pragma unroll 1
     for (int j = 0; j < kNChunk; ++j) {
-      // GELU(hidden chunk j) -> 16-bit H tile
-#pragma unroll 1
-      for (int gg = 0; gg < 6; ++gg) {
-        const int col = id.half * 48 + gg * 8;
-        float v[8];
-        tmem_ld8(tcol(t_a, id, col), v);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = gelu_as(v[e] + V->b1f[j * kNH + col + e]);
-        *reinterpret_cast<uint4 *>(hbuf + cm_offset(id.tok, col, kRS96, kCS)) = pack16x8<F16>(v);
+      mbar_wait(&bar, ph);   // W1 chunk j done (and W2 chunk j-1: hbuf and its weight buffer are free)
+      ph ^= 1;
+      tc_fence_after();
+      cp_async_wait<0>();    // {W1_{j+1}, W2_j}
+      fence_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (threadIdx.x == 0 && j + 1 < kNChunk) {
+        tc_fence_after();
+        issue_mma1(j + 1);
       }
-      cp_async_wait<0>();   // W chunk j+1 (issued one chunk ago)
+      if (j + 2 < kNChunk) cp_async_block(w1b + (j & 1) * kW1c, tcw + L.w1 + (size_t)(j + 2) * kW1c, kW1c, kTcThreads);
+      if (j + 1 < kNChunk)
+        cp_async_block(w2b + ((j + 1) & 1) * kW2c, tcw + L.w2 + (size_t)(j + 1) * kW2c, kW2c, kTcThreads);
+      cp_async_commit();
+      // GELU(hidden chunk j) -> 16-bit H tile
+      {
+        const int col = id.third * 32;
+        float v[32];
+        tmem_ld32(tcol(t_h[j & 1], id.q4, col), v);
+        uint8_t *dst = hbuf + cm_offset(id.tok, col, kRS96, kCS);
+        const float *bb = V->b1p + j * kNH + col;
+#pragma unroll
+        for (int gg = 0; gg < 4; ++gg) {
+          uint4 w4;
+          w4.x = gelu_pair<F16>(v[gg * 8 + 0] + bb[gg * 8 + 0], v[gg * 8 + 1] + bb[gg * 8 + 1]);
+          w4.y = gelu_pair<F16>(v[gg * 8 + 2] + bb[gg * 8 + 2], v[gg * 8 + 3] + bb[gg * 8 + 3]);
+          w4.z = gelu_pair<F16>(v[gg * 8 + 4] + bb[gg * 8 + 4], v[gg * 8 + 5] + bb[gg * 8 + 5]);
+          w4.w = gelu_pair<F16>(v[gg * 8 + 6] + bb[gg * 8 + 6], v[gg * 8 + 7] + bb[gg * 8 + 7]);
+          *reinterpret_cast<uint4 *>(dst + gg * kCS) = w4;
+        }
+      }
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
       if (threadIdx.x == 0) {
         tc_fence_after();
-        const uint8_t *wcur = (j & 1) ? wb1 : wb0, *wnext = (j & 1) ? wb0 : wb1;
-        const uint32_t hh = smem_u32(hbuf), w2 = smem_u32(wcur) + kW1c;
+        const uint32_t hh = smem_u32(hbuf), w2 = smem_u32(w2b + (j & 1) * kW2c);
 #pragma unroll
         for (int s = 0; s < kNH / 16; ++s)
           umma_bf16(t_y, make_desc(hh + s * 2 * kCS, kCS, kRS96), make_desc(w2 + s * 2 * kCS, kCS, kRS96), idesc144,
                     (j > 0 || s > 0));
-        if (j + 1 < kNChunk) {
-          const uint32_t aa = smem_u32(a), w1 = smem_u32(wnext);
-#pragma unroll
-          for (int s = 0; s < kKP / 16; ++s)
-            umma_bf16(t_a, make_desc(aa + s * 2 * kCS, kCS, kRS144), make_desc(w1 + s * 2 * kCS, kCS, kRS144),
-                      idesc96, s > 0);
-        }
-        umma_commit(&bar);
+        umma_commit(&bar);   // completes when W1 chunk j+1 (issued above) and this W2 chunk are both done
       }
-      mbar_wait(&bar, ph);
-      ph ^= 1;
-      tc_fence_after();
-      // chunk j's weight buffer is free: prefetch chunk j+2 into it
-      if (j + 2 < kNChunk) cp_async_block((j & 1) ? wb1 : wb0, tcw + L.wc + (size_t)(j + 2) * kWc, kWc);
-      cp_async_commit();
     }
+    mbar_wait(&bar, ph);
+    ph ^= 1;
+    tc_fence_after();
     // ---- y = u + s_m * (mlp + b_2) ----
     {
+      float v[48];
+      tmem_ld48(tcol(t_y, id.q4, col_lo), v);
       float *yb = y + (size_t)b * kC * Tout + t0 + id.tok;
 #pragma unroll
-      for (int gg = 0; gg < 9; ++gg) {
-        float v[8];
-        tmem_ld8(tcol(t_y, id, col_lo + gg * 8), v);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int n = col_lo + gg * 8 + e;
-          if (n < kC && live) yb[(size_t)n * Tout] = fmaf(V->sm[n], v[e] + V->b2[n], u[gg * 8 + e]);
-        }
+      for (int i = 0; i < 48; ++i) {
+        const int n = col_lo + i;
+        if (n < kC && live) yb[(size_t)n * Tout] = fmaf(V->sm[n], v[i] + V->b2[n], u[i]);
       }
     }
     cp_async_wait<0>();
@@ -795,31 +804,51 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__rest
 }
 
 // ------------------------------------------------------------------ weight packing
+// operand image of src[row0 + r][col0 + k] * colscale[col0 + k]   (zero padded)
 template <bool F16>
 __global__ void pack_image_kernel(const float *__restrict__ src, int ld, int row0, int col0, int rows_valid,
-                                  int cols_valid, uint8_t *__restrict__ dst, int rows_pad, int cols_pad) {
+                                  int cols_valid, const float *__restrict__ colscale, uint8_t *__restrict__ dst,
+                                  int rows_pad, int cols_pad) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= rows_pad * cols_pad) return;
   const int r = e / cols_pad, k = e % cols_pad;
-  const float v = (r < rows_valid && k < cols_valid) ? src[(size_t)(row0 + r) * ld + col0 + k] : 0.f;
+  float v = 0.f;
+  if (r < rows_valid && k < cols_valid) {
+    v = src[(size_t)(row0 + r) * ld + col0 + k];
+    if (colscale) v *= colscale[col0 + k];
+  }
   *reinterpret_cast<unsigned short *>(dst + cm_offset(r, k, (cols_pad / 8) * 128, 128)) = to16<F16>(v);
 }
-__global__ void pack_b1_kernel(const float *__restrict__ src, float *__restrict__ dst) {
+// out[n] = bias[n] + sum_c w[n][c] * lnb[c]  (n < rows), 0 for the padding
+__global__ void fold_bias_kernel(const float *__restrict__ w, const float *__restrict__ bias,
+                                 const float *__restrict__ lnb, float *__restrict__ out, int rows, int cols,
+                                 int rows_pad) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= rows_pad) return;
+  float acc = 0.f;
+  if (n < rows) {
+    acc = bias[n];
+    for (int c = 0; c < cols; ++c) acc = fmaf(w[(size_t)n * cols + c], lnb[c], acc);
+  }
+  out[n] = acc;
+}
+__global__ void scale_cols_kernel(const float *__restrict__ w, const float *__restrict__ g, float *__restrict__ out,
+                                  int rows, int cols) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < kHidPad) dst[e] = e < 4 * kC ? src[e] : 0.f;
+  if (e < rows * cols) out[e] = w[e] * g[e % cols];
 }
 
-void pack_image(bool f16, const float *src, int ld, int row0, int col0, int rv, int cv, uint8_t *dst, int rp,
-                int cp, cudaStream_t st) {
+void pack_image(bool f16, const float *src, int ld, int row0, int col0, int rv, int cv, const float *colscale,
+                uint8_t *dst, int rp, int cp, cudaStream_t st) {
   if (f16)
-    pack_image_kernel<true><<<ceil_div(rp * cp, 256), 256, 0, st>>>(src, ld, row0, col0, rv, cv, dst, rp, cp);
+    pack_image_kernel<true><<<ceil_div(rp * cp, 256), 256, 0, st>>>(src, ld, row0, col0, rv, cv, colscale, dst, rp, cp);
   else
-    pack_image_kernel<false><<<ceil_div(rp * cp, 256), 256, 0, st>>>(src, ld, row0, col0, rv, cv, dst, rp, cp);
+    pack_image_kernel<false><<<ceil_div(rp * cp, 256), 256, 0, st>>>(src, ld, row0, col0, rv, cv, colscale, dst, rp, cp);
 }
 
 constexpr size_t kFrontSmem = (size_t)kC * kXLD * 4 + 2 * kTile144 + kW144 + sizeof(FrontVec);
 constexpr size_t kApplySmem = (size_t)kTile144 + kW144;
-constexpr size_t kBackSmem = (size_t)kTile144 + kHTile + kW144 + 2 * kWc + sizeof(BackVec);
+constexpr size_t kBackSmem = (size_t)kTile144 + kHTile + kW144 + 2 * kW1c + 2 * kW2c + sizeof(BackVec);
 static_assert(kFrontSmem <= 226 * 1024, "tc_front shared memory");
 static_assert(kBackSmem <= 226 * 1024, "tc_back shared memory");
 
@@ -829,8 +858,13 @@ int forward_tc_t(const void *packed_fp32, const void *packed_tc, const float *x,
   const TcWorkspace W = tc_workspace(b, t, stride);
   const BlockPack P = block_pack_view(packed_fp32, kC);
   constexpr TcPack L = tc_pack_layout();
-  const uint8_t *tcw = static_cast<const uint8_t *>(packed_tc) + (F16 ? L.img_bytes : 0);
-  const float *b1f = reinterpret_cast<const float *>(static_cast<const uint8_t *>(packed_tc) + L.b1f);
+  const uint8_t *base = static_cast<const uint8_t *>(packed_tc);
+  const uint8_t *tcw = base + (F16 ? L.img_bytes : 0);
+  const float *wvp = reinterpret_cast<const float *>(base + L.wvp);
+  const float *bvp = reinterpret_cast<const float *>(base + L.bvp);
+  const float *bqp = reinterpret_cast<const float *>(base + L.bqp);
+  const float *bkp = reinterpret_cast<const float *>(base + L.bkp);
+  const float *b1p = reinterpret_cast<const float *>(base + L.b1p);
   uint8_t *ws = static_cast<uint8_t *>(ws_tc);
   float *gram = reinterpret_cast<float *>(ws + W.gram_part);
   float *beff = reinterpret_cast<float *>(ws + W.beff);
@@ -847,20 +881,22 @@ int forward_tc_t(const void *packed_fp32, const void *packed_tc, const float *x,
   {
     LaunchScope ls(K_TC_FRONT, st);
     tc_front_kernel<F16><<<dim3(W.nchunk, b), kTcThreads, kFrontSmem, st>>>(
-        P, tcw, x, gram, vn, t, W.tout, stride, W.tiles, W.tiles_per_chunk, W.nchunk, 1.0f / sqrtf((float)kHS));
+        P, tcw, bqp, bkp, x, gram, vn, t, W.tout, stride, W.tiles, W.tiles_per_chunk, W.nchunk,
+        1.0f / sqrtf((float)kHS));
   }
   {
     LaunchScope ls(K_BLOCK_FOLD, st);
-    tc_fold_kernel<F16><<<dim3(b, 4), 256, 0, st>>>(P, gram, W.nchunk, weff, beff);
+    block_fold_kernel<kC, F16 ? 2 : 1><<<dim3(b, FoldCfg<kC>::NBLK), kFoldThreads, 0, st>>>(wvp, bvp, gram, W.nchunk,
+                                                                                           weff, beff, kKP, kKP);
   }
   {
     LaunchScope ls(K_TC_APPLY, st);
-    tc_apply_kernel<F16><<<dim3(W.tiles, b), kTcThreads, kApplySmem, st>>>(vn, weff, beff, obuf, W.tout, W.tiles);
+    tc_apply_kernel<F16><<<dim3(W.tiles, b), kApplyThreads, kApplySmem, st>>>(vn, weff, beff, obuf, W.tout, W.tiles);
   }
   {
     LaunchScope ls(K_TC_BACK, st);
     const int total = b * W.tiles;
-    tc_back_kernel<F16><<<min(total, num_sms()), kTcThreads, kBackSmem, st>>>(P, tcw, b1f, x, obuf, y, b, t, W.tout,
+    tc_back_kernel<F16><<<min(total, num_sms()), kTcThreads, kBackSmem, st>>>(P, tcw, b1p, x, obuf, y, b, t, W.tout,
                                                                              stride, W.tiles);
   }
   return check_launch("block_forward_tc");
@@ -874,20 +910,27 @@ size_t block_tc_packed_bytes(int c) { return c == kC ? align_up(tc_pack_layout()
 int block_tc_pack(const otp_block_params *p, int c, void *packed_tc, cudaStream_t st) {
   if (c != kC) return OTP_OK;
   constexpr TcPack L = tc_pack_layout();
-  LaunchScope ls(K_PACK, st, 31);
+  uint8_t *base = static_cast<uint8_t *>(packed_tc);
+  LaunchScope ls(K_PACK, st, 35);
   for (int f = 0; f < 2; ++f) {
-    uint8_t *d = static_cast<uint8_t *>(packed_tc) + f * L.img_bytes;
-    pack_image(f, p->q_w, kC, 0, 0, kC, kC, d + L.wq, kKP, kKP, st);
-    pack_image(f, p->k_w, kC, 0, 0, kC, kC, d + L.wk, kKP, kKP, st);
-    pack_image(f, p->proj_w, kC, 0, 0, kC, kC, d + L.wp, kKP, kKP, st);
+    uint8_t *d = base + f * L.img_bytes;
+    // LN_q / LN_k / LN2 affine folded in: W' = W diag(g), b' = b + W beta (fp32 vectors below)
+    pack_image(f, p->q_w, kC, 0, 0, kC, kC, p->q_norm_w, d + L.wq, kKP, kKP, st);
+    pack_image(f, p->k_w, kC, 0, 0, kC, kC, p->k_norm_w, d + L.wk, kKP, kKP, st);
+    pack_image(f, p->proj_w, kC, 0, 0, kC, kC, nullptr, d + L.wp, kKP, kKP, st);
     for (int j = 0; j < kNChunk; ++j) {
       const int hv = min(kNH, 4 * kC - j * kNH);
-      pack_image(f, p->mlp0_w, kC, j * kNH, 0, hv, kC, d + L.wc + (size_t)j * kWc, kNH, kKP, st);
-      pack_image(f, p->mlp3_w, 4 * kC, 0, j * kNH, kC, hv, d + L.wc + (size_t)j * kWc + kW1c, kKP, kNH, st);
+      pack_image(f, p->mlp0_w, kC, j * kNH, 0, hv, kC, p->ln2_w, d + L.w1 + (size_t)j * kW1c, kNH, kKP, st);
+      pack_image(f, p->mlp3_w, 4 * kC, 0, j * kNH, kC, hv, nullptr, d + L.w2 + (size_t)j * kW2c, kKP, kNH, st);
     }
   }
-  pack_b1_kernel<<<ceil_div(kHidPad, 256), 256, 0, st>>>(
-      p->mlp0_b, reinterpret_cast<float *>(static_cast<uint8_t *>(packed_tc) + L.b1f));
+  scale_cols_kernel<<<ceil_div(kC * kC, 256), 256, 0, st>>>(p->v_w, p->v_norm_w, reinterpret_cast<float *>(base + L.wvp),
+                                                            kC, kC);
+  fold_bias_kernel<<<1, 256, 0, st>>>(p->v_w, p->v_b, p->v_norm_b, reinterpret_cast<float *>(base + L.bvp), kC, kC, kKP);
+  fold_bias_kernel<<<1, 256, 0, st>>>(p->q_w, p->q_b, p->q_norm_b, reinterpret_cast<float *>(base + L.bqp), kC, kC, kKP);
+  fold_bias_kernel<<<1, 256, 0, st>>>(p->k_w, p->k_b, p->k_norm_b, reinterpret_cast<float *>(base + L.bkp), kC, kC, kKP);
+  fold_bias_kernel<<<ceil_div(kHidPad, 256), 256, 0, st>>>(p->mlp0_w, p->mlp0_b, p->ln2_b,
+                                                           reinterpret_cast<float *>(base + L.b1p), 4 * kC, kC, kHidPad);
   return check_launch("block_tc_pack");
 }
 

@@ -42,6 +42,7 @@ conv2d_kernel(const float *__restrict__ x, long long x_bs, const float *__restri
 #pragma unroll
   for (int o = 0; o < kCvCO; ++o) acc[o] = 0.f;
 
+#pragma unroll 4
   for (int ci = 0; ci < Cin; ++ci) {
     const float *__restrict__ xc = xb + (size_t)ci * P;
     const float *__restrict__ xac = xab ? xab + (size_t)ci * P : nullptr;
@@ -80,6 +81,105 @@ conv2d_kernel(const float *__restrict__ x, long long x_bs, const float *__restri
   }
 }
 
+// 3x3, dilation 1, few channels (the ten dense-connected branch convs of an RSB block):
+// a strip of TH image rows (+1 halo row each side) of every input channel is staged in
+// shared memory by coalesced loads that are all in flight at once, then each thread
+// produces every output channel of its pixels from shared memory.
+constexpr int kStripThreads = 256;
+
+template <int CO>
+__global__ void __launch_bounds__(kStripThreads)
+conv3x3_strip_kernel(const float *__restrict__ x, long long x_bs, const float *__restrict__ xa, long long xa_bs,
+                     const float *__restrict__ weight, const float *__restrict__ bias,
+                     const float *__restrict__ res, long long res_bs, float *__restrict__ y, long long y_bs,
+                     int Cin, int H, int W, int Cout, int TH, int relu) {
+  extern __shared__ float sm[];
+  const int WP = W + 2, plane = (TH + 2) * WP;
+  float *xs = sm;                       // [Cin][TH+2][W+2]
+  float *ws = sm + ((Cin * plane + 3) & ~3);   // [Cin*9][CO]
+  const int h0 = blockIdx.x * TH, b = blockIdx.y;
+  const int P = H * W;
+  for (int e = threadIdx.x; e < Cin * 9 * CO; e += kStripThreads) {
+    const int o = e % CO, ck = e / CO;
+    ws[e] = o < Cout ? __ldg(weight + (size_t)o * Cin * 9 + ck) : 0.f;
+  }
+  const float *xb = x + (size_t)b * x_bs;
+  const float *xab = xa ? xa + (size_t)b * xa_bs : nullptr;
+  for (int e = threadIdx.x; e < Cin * plane; e += kStripThreads) {
+    const int ci = e / plane, r = (e % plane) / WP, c = e % WP;
+    const int hh = h0 - 1 + r, ww = c - 1;
+    float v = 0.f;
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+      v = __ldg(xb + (size_t)ci * P + hh * W + ww);
+      if (xab) v += __ldg(xab + (size_t)ci * P + hh * W + ww);
+    }
+    xs[e] = v;
+  }
+  __syncthreads();
+  const int rows = min(TH, H - h0);
+  for (int pix = threadIdx.x; pix < rows * W; pix += kStripThreads) {
+    const int ty = pix / W, tx = pix % W;
+    float acc[CO];
+#pragma unroll
+    for (int o = 0; o < CO; ++o) acc[o] = 0.f;
+    for (int ci = 0; ci < Cin; ++ci) {
+      const float *xp = xs + ci * plane + ty * WP + tx;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const float v = xp[i * WP + j];
+          const float4 *wr = reinterpret_cast<const float4 *>(ws + (ci * 9 + i * 3 + j) * CO);
+#pragma unroll
+          for (int q = 0; q < CO / 4; ++q) {
+            const float4 w4 = wr[q];
+            acc[4 * q + 0] = fmaf(w4.x, v, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(w4.y, v, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(w4.z, v, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(w4.w, v, acc[4 * q + 3]);
+          }
+        }
+    }
+    const int p = (h0 + ty) * W + tx;
+#pragma unroll
+    for (int o = 0; o < CO; ++o) {
+      if (o < Cout) {
+        float v = acc[o] + (bias ? __ldg(bias + o) : 0.f);
+        if (res) v += __ldg(res + (size_t)b * res_bs + (size_t)o * P + p);
+        if (relu) v = fmaxf(v, 0.f);
+        y[(size_t)b * y_bs + (size_t)o * P + p] = v;
+      }
+    }
+  }
+}
+
+template <int CO>
+static bool launch_strip(const float *x, long long x_bs, const float *xa, long long xa_bs, const float *weight,
+                         const float *bias, const float *res, long long res_bs, float *y, long long y_bs, int b,
+                         int cin, int h, int w, int cout, int relu, cudaStream_t st) {
+  // strip height: fill the 256 threads' pixel rounds as evenly as possible
+  int th = 2;
+  float best = 0.f;
+  for (int t = 2; t <= 8; ++t) {
+    const int px = t * w;
+    const float eff = (float)px / (float)(ceil_div(px, kStripThreads) * kStripThreads) + 0.01f * t;
+    if (eff > best) {
+      best = eff;
+      th = t;
+    }
+  }
+  const size_t smem = ((size_t)((cin * (th + 2) * (w + 2) + 3) & ~3) + (size_t)cin * 9 * CO) * sizeof(float);
+  if (smem > 160 * 1024) return false;
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaFuncSetAttribute(conv3x3_strip_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = smem;
+  }
+  conv3x3_strip_kernel<CO><<<dim3(ceil_div(h, th), b), kStripThreads, smem, st>>>(
+      x, x_bs, xa, xa_bs, weight, bias, res, res_bs, y, y_bs, cin, h, w, cout, th, relu);
+  return true;
+}
+
 }  // namespace otp
 
 using namespace otp;
@@ -104,6 +204,19 @@ extern "C" int otp_conv2d(const float *x, long long x_bstride, const float *x_ad
   dim3 grid(ceil_div(h * w, kCvThreads), ceil_div(cout, kCvCO), b);
   cudaStream_t st = (cudaStream_t)stream;
   LaunchScope ls(K_CONV2D, st);
+  if (k == 3 && dilation == 1 && cin <= 32 && cout <= 24 && w <= 510) {
+    bool ok = false;
+    if (cout <= 8)
+      ok = launch_strip<8>(x, x_bstride, x_add, x_add_bstride, weight, bias, residual, residual_bstride, y,
+                           y_bstride, b, cin, h, w, cout, relu, st);
+    else if (cout <= 16)
+      ok = launch_strip<16>(x, x_bstride, x_add, x_add_bstride, weight, bias, residual, residual_bstride, y,
+                            y_bstride, b, cin, h, w, cout, relu, st);
+    else
+      ok = launch_strip<24>(x, x_bstride, x_add, x_add_bstride, weight, bias, residual, residual_bstride, y,
+                            y_bstride, b, cin, h, w, cout, relu, st);
+    if (ok) return check_launch("conv3x3_strip_kernel");
+  }
   if (k == 1) {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(conv2d_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -127,6 +127,7 @@ pyramid_conv_kernel(const float *__restrict__ s0, const float *__restrict__ s1,
   const float *p0 = s0 + (size_t)b * C * T + t;
   const float *p1 = s1 + (size_t)b * C * T1;
   const float *p2 = s2 + (size_t)b * C * T2;
+#pragma unroll 8
   for (int c = 0; c < C; ++c) {
     float v0 = __ldg(p0 + (size_t)c * T);
     float v1 = (1.f - la) * __ldg(p1 + (size_t)c * T1 + a0) + la * __ldg(p1 + (size_t)c * T1 + a1);
