@@ -78,22 +78,25 @@ def block_tokens(t):
     return enc + enc + [(J, t)] * 6
 
 
-def algorithmic_work(b, t=T):
+def algorithmic_work(b, t=T, precision="fp32"):
     """kernel name -> (bound, work per step): FLOPs (2*MAC) for tensor-bound kernels,
-    bytes for HBM-bound ones."""
+    bytes for HBM-bound ones.  In the 16-bit modes the C=136 blocks run the tc_* kernels and
+    the block_* (CUDA-core) kernels only see the C=17 flow encoder."""
     blocks = block_tokens(t)
     big = [(c, tt) for c, tt in blocks if c == C8]
+    simt = blocks if precision == "fp32" else [(c, tt) for c, tt in blocks if c != C8]
     w = {}
     flops = lambda f, bl: float(sum(f(c, tt) for c, tt in bl)) * b   # noqa: E731
-    w["block_front"] = ("tensor", flops(lambda c, tt: (4 * c * c + 2 * c * (c // (2 if c == C8 else 1))) * tt, blocks))
-    w["block_apply"] = ("tensor", flops(lambda c, tt: 2 * c * c * tt, blocks))
-    w["block_back"] = ("tensor", flops(lambda c, tt: 18 * c * c * tt, blocks))
+    w["block_front"] = ("tensor", flops(lambda c, tt: (4 * c * c + 2 * c * (c // (2 if c == C8 else 1))) * tt, simt))
+    w["block_apply"] = ("tensor", flops(lambda c, tt: 2 * c * c * tt, simt))
+    w["block_back"] = ("tensor", flops(lambda c, tt: 18 * c * c * tt, simt))
     w["tc_block_front"] = ("tensor", flops(lambda c, tt: (4 * c * c + 2 * c * (c // 2)) * tt, big))
     w["tc_block_apply"] = ("tensor", flops(lambda c, tt: 2 * c * c * tt, big))
     w["tc_block_back"] = ("tensor", flops(lambda c, tt: 18 * c * c * tt, big))
-    # conv2d launches: 2 RSB chains + 5 x (offset, mask) convs  (BASELINE.md section 3)
-    w["conv2d"] = ("tensor", (0.116e9 + 0.868e9 + 5 * (1.218e9 + 0.609e9)) * t / T * b)
-    w["tc_offset_mask_conv"] = ("tensor", 5 * (1.218e9 + 0.609e9) * t / T * b)
+    rsb = (0.116e9 + 0.868e9) * t / T * b                      # BASELINE.md section 3
+    offmask = 5 * (1.218e9 + 0.609e9) * t / T * b
+    w["conv2d"] = ("tensor", rsb + offmask if precision == "fp32" else rsb)
+    w["tc_offset_mask_dcn"] = ("tensor", offmask + 5 * 0.036e9 * t / T * b)
     # HBM-bound: read offsets+masks (459 ch) + x (17) + write/accumulate out (17), fp32, x5 dilations
     w["mdcn_fwd"] = ("hbm", 5.0 * (459 + 17 + 17) * t * 4 * b)
     w["final_preds"] = ("hbm", float(J * t * 4 + J * 28) * b)
@@ -288,7 +291,7 @@ def run_b200(args):
 
     if rank == 0:
         peaks = load_peaks()
-        work = algorithmic_work(b)
+        work = algorithmic_work(b, precision=precision)
         kernels = {}
         for name, (tot_ms, cnt) in prof.items():
             per_step = tot_ms / args.steps

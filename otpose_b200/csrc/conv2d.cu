@@ -105,15 +105,26 @@ conv3x3_strip_kernel(const float *__restrict__ x, long long x_bs, const float *_
   }
   const float *xb = x + (size_t)b * x_bs;
   const float *xab = xa ? xa + (size_t)b * xa_bs : nullptr;
-  for (int e = threadIdx.x; e < Cin * plane; e += kStripThreads) {
-    const int ci = e / plane, r = (e % plane) / WP, c = e % WP;
-    const int hh = h0 - 1 + r, ww = c - 1;
-    float v = 0.f;
-    if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
-      v = __ldg(xb + (size_t)ci * P + hh * W + ww);
-      if (xab) v += __ldg(xab + (size_t)ci * P + hh * W + ww);
+  constexpr int U = 8;   // independent loads in flight per thread (a load->store loop serialises on latency)
+  for (int base = threadIdx.x; base < Cin * plane; base += U * kStripThreads) {
+    float v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = base + u * kStripThreads;
+      const int ci = e / plane, r = (e % plane) / WP, c = e % WP;
+      const int hh = h0 - 1 + r, ww = c - 1;
+      float val = 0.f;
+      if (e < Cin * plane && hh >= 0 && hh < H && ww >= 0 && ww < W) {
+        val = __ldg(xb + (size_t)ci * P + hh * W + ww);
+        if (xab) val += __ldg(xab + (size_t)ci * P + hh * W + ww);
+      }
+      v[u] = val;
     }
-    xs[e] = v;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = base + u * kStripThreads;
+      if (e < Cin * plane) xs[e] = v[u];
+    }
   }
   __syncthreads();
   const int rows = min(TH, H - h0);

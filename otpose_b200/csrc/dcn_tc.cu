@@ -24,7 +24,7 @@ using namespace tc;
 
 namespace {
 constexpr int kJ = 17, kCin = 32, kTaps = 9;
-constexpr int kTM = 128, kThreads = 256;
+constexpr int kTM = 128, kThreads = 384;   // thread = (pixel, third): 3 taps / 3 joints each
 constexpr int kNPad = 256;                        // UMMA N (>= 27 * 9 = 243)
 constexpr uint32_t kCS = 128, kRS32 = (kCin / 8) * 128;   // 512
 constexpr uint32_t kATap = (kTM / 8) * kRS32;     // 8192   [128 px][32 ch]
@@ -64,7 +64,7 @@ tc_dcn_fused_kernel(const uint8_t *__restrict__ wimg, const float *__restrict__ 
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q4 = warp & 3, half = warp >> 2, tok = q4 * 32 + lane;
+  const int q4 = warp & 3, third = warp >> 2, tok = q4 * 32 + lane;
   const int P = H * W;
 
   for (uint32_t o = threadIdx.x * 16; o < kWSlice; o += kThreads * 16) cp_async16(ws + o, wimg + o);
@@ -85,8 +85,8 @@ tc_dcn_fused_kernel(const uint8_t *__restrict__ wimg, const float *__restrict__ 
   const uint32_t tm = tmem_slot;
   const uint32_t idesc = make_idesc_16(kNPad, false, false, F16 ? 0u : 1u);
   uint32_t ph = 0;
-  // joints of this thread in the DCN phase: the CTA's nj joints split over the two thread halves
-  const int jl_lo = half ? (nj + 1) / 2 : 0, jl_hi = half ? nj : (nj + 1) / 2;
+  // joints of this thread in the DCN phase: the CTA's nj joints split over the three thread thirds
+  const int jl_lo = 3 * third, jl_hi = min(nj, 3 * third + 3);
   const int msk_col0 = 18 * nj;
 
   for (int g = blockIdx.x; g < B * tiles; g += gridDim.x) {
@@ -94,20 +94,21 @@ tc_dcn_fused_kernel(const uint8_t *__restrict__ wimg, const float *__restrict__ 
     const int p = tile * kTM + tok;
     const bool live = p < P;
     const int h = live ? p / W : 0, w = live ? p % W : 0;
-    // ---- im2col: 9 dilated taps of the 32-channel feature, this thread's 16 channels ----
+    // ---- im2col: this thread's 3 of the 9 dilated taps, all 32 channels (96 loads in flight) ----
     {
-      const float *tb = trans + ((size_t)b * kCin + half * 16) * P;
-#pragma unroll 3
-      for (int t = 0; t < kTaps; ++t) {
+      const float *tb = trans + (size_t)b * kCin * P;
+#pragma unroll
+      for (int tt = 0; tt < 3; ++tt) {
+        const int t = 3 * third + tt;
         const int hh = h + (t / 3 - 1) * dil, ww = w + (t % 3 - 1) * dil;
         const bool ok = live && hh >= 0 && hh < H && ww >= 0 && ww < W;
         const float *src = tb + (ok ? hh * W + ww : 0);
-        float v[16];
+        float v[kCin];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) v[c] = ok ? __ldg(src + (size_t)c * P) : 0.f;
-        uint8_t *dst = as + t * kATap + cm_offset(tok, half * 16, kRS32, kCS);
-        *reinterpret_cast<uint4 *>(dst) = pack16x8<F16>(v);
-        *reinterpret_cast<uint4 *>(dst + kCS) = pack16x8<F16>(v + 8);
+        for (int c = 0; c < kCin; ++c) v[c] = ok ? __ldg(src + (size_t)c * P) : 0.f;
+        uint8_t *dst = as + t * kATap + cm_offset(tok, 0, kRS32, kCS);
+#pragma unroll
+        for (int g = 0; g < kCin / 8; ++g) *reinterpret_cast<uint4 *>(dst + g * kCS) = pack16x8<F16>(v + 8 * g);
       }
     }
     fence_async_smem();
@@ -150,42 +151,66 @@ tc_dcn_fused_kernel(const uint8_t *__restrict__ wimg, const float *__restrict__ 
       }
       if (live) {
         const float *img = xb + (size_t)(j0 + jl) * P;
+        // Branch-free bilinear taps (same arithmetic as dmcn_im2col_bilinear): out-of-range corners
+        // get weight 0 and a clamped address, so the 12 loads of a tap triple are independent
+        // and in flight together instead of sitting behind data-dependent branches.
 #pragma unroll
-        for (int t = 0; t < kTaps; ++t) {
-          const float h_im = (float)(h + (t / 3 - 1) * dil) + off[2 * t];
-          const float w_im = (float)(w + (t % 3 - 1) * dil) + off[2 * t + 1];
-          float val = 0.f;
-          if (h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W) {
-            const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
-            const int h_high = h_low + 1, w_high = w_low + 1;
-            const float lh = h_im - (float)h_low, lw = w_im - (float)w_low;
-            const float hh = 1.f - lh, hw = 1.f - lw;
-            float v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f;
-            if (h_low >= 0 && w_low >= 0) v1 = __ldg(img + h_low * W + w_low);
-            if (h_low >= 0 && w_high <= W - 1) v2 = __ldg(img + h_low * W + w_high);
-            if (h_high <= H - 1 && w_low >= 0) v3 = __ldg(img + h_high * W + w_low);
-            if (h_high <= H - 1 && w_high <= W - 1) v4 = __ldg(img + h_high * W + w_high);
-            val = (hh * hw) * v1 + (hh * lw) * v2 + (lh * hw) * v3 + (lh * lw) * v4;
+        for (int tg = 0; tg < 3; ++tg) {
+          float wgt[3][4];
+          int adr[3][4];
+#pragma unroll
+          for (int u = 0; u < 3; ++u) {
+            const int t = 3 * tg + u;
+            const float h_im = (float)(h + (t / 3 - 1) * dil) + off[2 * t];
+            const float w_im = (float)(w + (t % 3 - 1) * dil) + off[2 * t + 1];
+            const bool in = h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W;
+            const float hf = floorf(fminf(fmaxf(h_im, -2.f), (float)H + 1.f));
+            const float wf = floorf(fminf(fmaxf(w_im, -2.f), (float)W + 1.f));
+            const int h_low = (int)hf, w_low = (int)wf;
+            const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
+            const bool h0 = in && h_low >= 0, h1 = in && h_low + 1 <= H - 1;
+            const bool w0 = w_low >= 0, w1 = w_low + 1 <= W - 1;
+            wgt[u][0] = (h0 && w0) ? hh * hw : 0.f;
+            wgt[u][1] = (h0 && w1) ? hh * lw : 0.f;
+            wgt[u][2] = (h1 && w0) ? lh * hw : 0.f;
+            wgt[u][3] = (h1 && w1) ? lh * lw : 0.f;
+            const int hc0 = min(max(h_low, 0), H - 1), hc1 = min(max(h_low + 1, 0), H - 1);
+            const int wc0 = min(max(w_low, 0), W - 1), wc1 = min(max(w_low + 1, 0), W - 1);
+            adr[u][0] = hc0 * W + wc0;
+            adr[u][1] = hc0 * W + wc1;
+            adr[u][2] = hc1 * W + wc0;
+            adr[u][3] = hc1 * W + wc1;
           }
-          const float col = val * msk[t];
-          const float *wr = wd + jl * 9 + t;
+          float val[3][4];
 #pragma unroll
-          for (int o = 0; o < kJ; ++o) acc[o] = fmaf(wr[o * 81], col, acc[o]);
+          for (int u = 0; u < 3; ++u)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) val[u][q] = __ldg(img + adr[u][q]);
+#pragma unroll
+          for (int u = 0; u < 3; ++u) {
+            const int t = 3 * tg + u;
+            const float v = wgt[u][0] * val[u][0] + wgt[u][1] * val[u][1] + wgt[u][2] * val[u][2] +
+                            wgt[u][3] * val[u][3];
+            const float col = v * msk[t];
+            const float *wr = wd + jl * 9 + t;
+#pragma unroll
+            for (int o = 0; o < kJ; ++o) acc[o] = fmaf(wr[o * 81], col, acc[o]);
+          }
         }
       }
     }
-    // ---- combine the two thread halves (exchange buffer aliases the dead im2col taps) ----
+    // ---- combine the three thread thirds (exchange buffer aliases the dead im2col taps) ----
     float *ex = reinterpret_cast<float *>(as);
-    if (half == 1) {
+    if (third > 0) {
 #pragma unroll
-      for (int o = 0; o < kJ; ++o) ex[o * kTM + tok] = acc[o];
+      for (int o = 0; o < kJ; ++o) ex[((third - 1) * kJ + o) * kTM + tok] = acc[o];
     }
     tc_fence_before();
     __syncthreads();
-    if (half == 0 && live) {
+    if (third == 0 && live) {
 #pragma unroll
       for (int o = 0; o < kJ; ++o) {
-        float v = acc[o] + ex[o * kTM + tok] + (dcn_b ? __ldg(dcn_b + o) : 0.f);
+        float v = acc[o] + ex[o * kTM + tok] + ex[(kJ + o) * kTM + tok] + (dcn_b ? __ldg(dcn_b + o) : 0.f);
         float *dst = out + ((size_t)b * kJ + o) * P + p;
         *dst = accumulate ? fmaf(alpha, v, *dst) : alpha * v;
       }
