@@ -29,9 +29,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-H, W, J = 96, 72, 17
+H, W, J = 96, 72, 17          # --heatmap HxW overrides H, W (BASELINE config 5: 128x96)
+FRAMES = 5                     # --frames 3|5|7 (config 5 window sweep; the reference has 5 only)
 C8 = 8 * J
-T = H * W
+T = 96 * 72                    # token count the per-clip FLOP constants below are quoted at
 METRIC = "temporal_head_person_clips_per_s"
 
 
@@ -45,7 +46,14 @@ def parse():
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16", "fp16"])
     ap.add_argument("--cpu-clips", type=int, default=2, help="clips per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--frames", type=int, default=5, choices=[3, 5, 7],
+                    help="frame window (config 5 sweep; 5 = the reference's supplement)")
+    ap.add_argument("--heatmap", default="96x72", help="heat-map HxW (config 5: 128x96)")
+    args = ap.parse_args()
+    global H, W, FRAMES
+    H, W = (int(v) for v in args.heatmap.lower().split("x"))
+    FRAMES = args.frames
+    return args
 
 
 def dist_env():
@@ -100,8 +108,8 @@ def algorithmic_work(b, t=T, precision="fp32"):
     # HBM-bound: read offsets+masks (459 ch) + x (17) + write/accumulate out (17), fp32, x5 dilations
     w["mdcn_fwd"] = ("hbm", 5.0 * (459 + 17 + 17) * t * 4 * b)
     w["final_preds"] = ("hbm", float(J * t * 4 + J * 28) * b)
-    w["fusion_sum"] = ("hbm", float((5 * J + J + 1) * t * 4) * b)
-    w["fusion_stack"] = ("hbm", float((5 * J + J + 1 + 2 * C8 + 2 * J) * t * 4) * b)
+    w["fusion_sum"] = ("hbm", float((FRAMES * J + J + 1) * t * 4) * b)
+    w["fusion_stack"] = ("hbm", float((FRAMES * J + J + 1 + 2 * C8 + 2 * J) * t * 4) * b)
     w["pyramid_conv1x1"] = ("hbm", 2.0 * (C8 * (t + t // 2 + t // 4) + J * t) * 4 * b)
     return w
 
@@ -171,7 +179,8 @@ def cpu_reference(clips, steps, warmup):
     torch.set_num_threads(threads)
     shapes = {k: v.shape for k, v in OTPose(default_cfg((H, W))).state_dict().items()}
     sd = syn.fill_state_dict(shapes, seed=2024)
-    rough, margin = syn.synth_rough_heatmaps(clips, J, H, W), syn.synth_margin(clips)
+    rough = syn.synth_rough_heatmaps(clips, J, H, W, frames=FRAMES)
+    margin = syn.synth_margin(clips, frames=FRAMES)
     center, scale = syn.synth_center_scale(clips)
 
     def step():
@@ -186,7 +195,7 @@ def cpu_reference(clips, steps, warmup):
         step()
     dt = time.perf_counter() - t0
     return {"value": clips * steps / dt, "unit": "clips/s", "cores": threads, "kind": "port",
-            "sample": f"{steps} steps x {clips} clips of the bench workload (96x72, 17 joints), torch CPU fp32 "
+            "sample": f"{steps} steps x {clips} clips of the bench workload ({FRAMES} frames, {H}x{W}, 17 joints), torch CPU fp32 "
                       f"oracle port, {threads} threads", "ms_per_step": 1e3 * dt / steps}
 
 
@@ -208,7 +217,7 @@ def run_reference(args):
 def workload_config(batch, precision):
     return {"workload": f"OTPose temporal head fwd (fusion prologue + flow/temporal ConvTransformer encoders + "
                         f"RSB + 5x offset/mask conv + modulated DCN + get_final_preds), {batch} person-clips/GPU, "
-                        f"5 frames, {H}x{W} heat maps, {J} joints (BASELINE configs[1] batch; HRNet backbone out of scope)",
+                        f"{FRAMES} frames, {H}x{W} heat maps, {J} joints (BASELINE configs[1] batch; HRNet backbone out of scope)",
             "clips_per_gpu": batch, "heatmap": [H, W], "joints": J, "precision": precision,
             "l2": "per-step working set (activations > 1 GB at 32 clips) far exceeds the 126 MB L2; no explicit flush"}
 
@@ -235,8 +244,8 @@ def run_b200(args):
     model = OTPose(default_cfg((H, W)), precision=precision)
     model.load_state_dict(syn.fill_state_dict({k: v.shape for k, v in model.state_dict().items()}, seed=2024))
     model = model.to(dev).eval()
-    rough_host = syn.synth_rough_heatmaps(b, J, H, W, seed=shard_seed(1234, rank)).pin_memory()
-    margin_host = syn.synth_margin(b, seed=shard_seed(1236, rank)).pin_memory()
+    rough_host = syn.synth_rough_heatmaps(b, J, H, W, frames=FRAMES, seed=shard_seed(1234, rank)).pin_memory()
+    margin_host = syn.synth_margin(b, seed=shard_seed(1236, rank), frames=FRAMES).pin_memory()
     center, scale = (torch.from_numpy(a).to(dev) for a in syn.synth_center_scale(b, seed=shard_seed(1237, rank)))
     rough, margin = rough_host.to(dev), margin_host.to(dev)
     rough_stage = torch.empty_like(rough)
@@ -291,7 +300,7 @@ def run_b200(args):
 
     if rank == 0:
         peaks = load_peaks()
-        work = algorithmic_work(b, precision=precision)
+        work = algorithmic_work(b, t=H * W, precision=precision)
         kernels = {}
         for name, (tot_ms, cnt) in prof.items():
             per_step = tot_ms / args.steps

@@ -91,6 +91,26 @@ int otp_mdcn_forward(const float *x, const float *offset, const float *mask, con
                      float alpha, int accumulate, otp_stream_t stream);
 
 /* ---------------------------------------------------------------------------
+ * a12 (native part)  modulated deformable convolution backward
+ * replaces modulated_deform_conv_cuda_backward (deform_conv_cuda.cpp:551-664)
+ * and deform_conv_cuda_kernel.cu:434-503, 573-705.  All gradients are
+ * overwritten (not accumulated).  grad_x is accumulated with 64-bit fixed-point
+ * atomics (scale 2^30) and is therefore bit-reproducible, unlike the
+ * reference's float atomicAdd; grad_weight/grad_bias are reduced in a fixed
+ * order.  grad_bias may be NULL.  Built for Cout == 17, groups == 1.
+ *   grad_out (B,Cout,Ho,Wo) -> grad_x (B,C,H,W), grad_offset / grad_mask shaped
+ *   like offset / mask, grad_weight (Cout,C,kh,kw), grad_bias (Cout).
+ * ------------------------------------------------------------------------- */
+size_t otp_mdcn_backward_workspace_bytes(int b, int c, int h, int w, int cout, int kh, int kw,
+                                         int stride, int pad, int dilation);
+int otp_mdcn_backward(const float *x, const float *offset, const float *mask, const float *weight,
+                      const float *grad_out, float *grad_x, float *grad_offset, float *grad_mask,
+                      float *grad_weight, float *grad_bias, int b, int c, int h, int w, int cout,
+                      int kh, int kw, int stride, int pad, int dilation, int groups,
+                      int deformable_groups, void *workspace, size_t workspace_bytes,
+                      otp_stream_t stream);
+
+/* ---------------------------------------------------------------------------
  * a1  fusion prologue, replaces model/OTPose.py:320-330 and :339-359.
  * rough (5B,J,T) ordered cur, prev, next, pprev, nnext.
  *   otp_fusion_sum    -> total_b (B,J,T), squeezed (B,T)  [the reference's
@@ -107,6 +127,18 @@ int otp_fusion_stack(const float *rough, const int64_t *margin, const float *squ
                      const float *context, const float *pe1, const float *pe2, int pe_stride, int b,
                      int j, int t, float *x1, float *x2, float *intersection, float *prev_b,
                      otp_stream_t stream);
+/* Window extension (BASELINE config 5, T = 3 / 5 / 7 frames): `frames` = 2*NP+1,
+ * rough (frames*B,J,T) ordered cur, prev1, next1, prev2, next2, ..., margin (B, 2*NP)
+ * in the same pair order.  prev_b / next_b sum every past / future frame,
+ * close_b the nearest pair, far_b the remaining pairs (far_b = cur at frames == 3).
+ * The reference has no code path for frames != 5 (`supplement = 5`,
+ * model/OTPose.py:188, 317-321); frames == 5 is exactly otp_fusion_sum / _stack. */
+int otp_fusion_sum_frames(const float *rough, int frames, int b, int j, int t, float *total_b,
+                          float *squeezed, otp_stream_t stream);
+int otp_fusion_stack_frames(const float *rough, const int64_t *margin, const float *squeezed,
+                            const float *context, const float *pe1, const float *pe2, int pe_stride,
+                            int frames, int b, int j, int t, float *x1, float *x2,
+                            float *intersection, float *prev_b, otp_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * a2-a5  ConvTransformer building blocks, replaces model/blocks.py:95-110

@@ -290,6 +290,46 @@ def fusion_prologue(rough_heatmaps, margin):
                 close_int=close_b * squeezed, far_int=far_b * squeezed)
 
 
+def fusion_prologue_frames(rough_heatmaps, margin):
+    """Window extension of ``fusion_prologue`` for BASELINE config 5 (T = 3 / 5 / 7 frames).
+
+    The reference hard-codes 5 frames (``supplement = 5``, model/OTPose.py:188, 317-321), so
+    this is a DEFINITION, not a restatement: frames ordered cur, prev1, next1, prev2, next2,
+    ...; margin (B, frames-1) in the same order; sums taken left to right so that the 5-frame
+    instance is the reference's expression bit for bit (tests/test_oracle.py asserts equality
+    with ``fusion_prologue``).  prev_b / next_b collect every past / future frame, close_b the
+    nearest pair, far_b the remaining pairs (= cur alone for 3 frames).
+    """
+    frames = margin.shape[1] + 1
+    assert frames % 2 == 1 and frames >= 3
+    B = rough_heatmaps.shape[0] // frames
+    fr = rough_heatmaps.split(B, dim=0)
+    cur, J = fr[0], fr[0].shape[1]
+    total_b = cur
+    for f in fr[1:]:
+        total_b = total_b + f
+    squeezed = torch.sum(total_b, axis=1)
+    squeezed = torch.stack([squeezed for _ in range(J)], dim=1)
+    sc = [torch.div(fr[i + 1], (margin.T[i] + 1)[:, None, None, None]) for i in range(frames - 1)]
+    prevs, nexts = sc[0::2], sc[1::2]
+    ps, ns = prevs[0], nexts[0]
+    for k in range(1, len(prevs)):
+        ps, ns = ps + prevs[k], ns + nexts[k]
+    prev_b, next_b = cur + ps, cur + ns
+    close_b = cur + (nexts[0] + prevs[0])
+    if len(prevs) >= 2:
+        fs = nexts[1] + prevs[1]
+        for k in range(2, len(prevs)):
+            fs = fs + (nexts[k] + prevs[k])
+        far_b = cur + fs
+    else:
+        far_b = cur.clone()
+    return dict(total_b=total_b, squeezed=squeezed, intersection=total_b * squeezed,
+                prev_b=prev_b, next_b=next_b, close_b=close_b, far_b=far_b,
+                prev_int=prev_b * squeezed, next_int=next_b * squeezed,
+                close_int=close_b * squeezed, far_int=far_b * squeezed)
+
+
 def head_forward(sd, rough_heatmaps, margin, dilations=(3, 6, 9, 12, 15), num_rsb_blocks=2,
                  return_intermediates=False):
     """OTPose.forward lines 320-394 (model/OTPose.py), given the backbone output.
@@ -297,9 +337,10 @@ def head_forward(sd, rough_heatmaps, margin, dilations=(3, 6, 9, 12, 15), num_rs
     Returns the reference 7-tuple (output_heatmaps, rough_heatmaps, intersection,
     prev_b, context_encoding, squeezed, total_b).
     """
-    B = rough_heatmaps.shape[0] // 5
+    frames = margin.shape[1] + 1           # 5 in the reference; 3 / 7 = the config-5 window extension
+    B = rough_heatmaps.shape[0] // frames
     J, H, W = rough_heatmaps.shape[1:]
-    f = fusion_prologue(rough_heatmaps, margin)
+    f = fusion_prologue(rough_heatmaps, margin) if frames == 5 else fusion_prologue_frames(rough_heatmaps, margin)
     ctx = conv_transformer(sd, "flow_encoder.", f["total_b"], 1, (0, 6, 0))
     context_encoding = torch.stack([s for s in ctx], dim=1).contiguous().view(B, J, H, W)
     x1 = torch.stack((f["intersection"], context_encoding, f["prev_b"], f["far_b"], f["close_b"],

@@ -42,8 +42,12 @@ SIGNATURES = {
     "otp_final_preds": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
     "otp_mdcn_forward": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32,
                                i32, i32, f32, i32, vp]),
+    "otp_mdcn_backward_workspace_bytes": (sz, [i32] * 10),
+    "otp_mdcn_backward": (i32, [vp] * 10 + [i32] * 12 + [vp, sz, vp]),
     "otp_fusion_sum": (i32, [vp, i32, i32, i32, vp, vp, vp]),
     "otp_fusion_stack": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
+    "otp_fusion_sum_frames": (i32, [vp, i32, i32, i32, i32, vp, vp, vp]),
+    "otp_fusion_stack_frames": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
     "otp_block_packed_bytes": (sz, [i32, i32]),
     "otp_block_pack": (i32, [C.POINTER(BlockParams), i32, i32, vp, sz, vp]),
     "otp_block_workspace_bytes": (sz, [i32, i32, i32, i32, i32, i32]),

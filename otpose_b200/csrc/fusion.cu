@@ -8,7 +8,12 @@ namespace otp {
 
 constexpr int kFuThreads = 256;
 
-// model/OTPose.py:324-326 -- total_b = cur+prev+next+pprev+nnext, squeezed = sum_j total_b
+// model/OTPose.py:324-326 -- total_b = cur+prev+next+pprev+nnext, squeezed = sum_j total_b.
+// NP = number of (prev_k, next_k) frame pairs around the current frame: the reference
+// hard-codes NP = 2 (`supplement = 5`, OTPose.py:188, 317-321); NP = 1 / 3 are the T=3 / T=7
+// window extension of BASELINE config 5, frames ordered cur, prev1, next1, prev2, next2, ...
+// and summed left to right, so NP = 2 is the reference's expression bit for bit.
+template <int NP>
 __global__ void __launch_bounds__(kFuThreads)
 fusion_sum_kernel(const float *__restrict__ rough, int B, int J, int T, float *__restrict__ total_b,
                   float *__restrict__ squeezed) {
@@ -20,7 +25,12 @@ fusion_sum_kernel(const float *__restrict__ rough, int B, int J, int T, float *_
   float sq = 0.f;
   for (int j = 0; j < J; ++j) {
     const float *rj = r + (size_t)j * T;
-    float tot = __ldg(rj) + __ldg(rj + fs) + __ldg(rj + 2 * fs) + __ldg(rj + 3 * fs) + __ldg(rj + 4 * fs);
+    float v[2 * NP + 1];
+#pragma unroll
+    for (int f = 0; f < 2 * NP + 1; ++f) v[f] = __ldg(rj + f * fs);
+    float tot = v[0];
+#pragma unroll
+    for (int f = 1; f < 2 * NP + 1; ++f) tot += v[f];
     total_b[((size_t)b * J + j) * T + t] = tot;
     sq += tot;
   }
@@ -28,6 +38,10 @@ fusion_sum_kernel(const float *__restrict__ rough, int B, int J, int T, float *_
 }
 
 // model/OTPose.py:330, 339-359 (+ pos_embd add of ConvVideoTransformer.py:140-155)
+//   prev_b  = cur + (prev1' + prev2' + ...)        next_b = cur + (next1' + next2' + ...)
+//   close_b = cur + (next1' + prev1')              far_b  = cur + sum_{k>=2} (next_k' + prev_k')
+// with x' = x / (margin + 1); NP = 2 gives the reference's lines 343-354, NP = 1 leaves far_b = cur.
+template <int NP>
 __global__ void __launch_bounds__(kFuThreads)
 fusion_stack_kernel(const float *__restrict__ rough, const int64_t *__restrict__ margin,
                     const float *__restrict__ squeezed, const float *__restrict__ context,
@@ -38,22 +52,40 @@ fusion_stack_kernel(const float *__restrict__ rough, const int64_t *__restrict__
   const int b = blockIdx.y;
   if (t >= T) return;
   const size_t fs = (size_t)B * J * T;
-  const float d0 = (float)(margin[4 * b + 0] + 1), d1 = (float)(margin[4 * b + 1] + 1);
-  const float d2 = (float)(margin[4 * b + 2] + 1), d3 = (float)(margin[4 * b + 3] + 1);
+  float den[2 * NP];
+#pragma unroll
+  for (int f = 0; f < 2 * NP; ++f) den[f] = (float)(margin[2 * NP * b + f] + 1);
   const float sq = __ldg(squeezed + (size_t)b * T + t);
   for (int j = 0; j < J; ++j) {
     const size_t o17 = ((size_t)b * J + j) * T + t;
     const float *rj = rough + o17;
-    float cur = __ldg(rj), prev = __ldg(rj + fs), next = __ldg(rj + 2 * fs);
-    float pprev = __ldg(rj + 3 * fs), nnext = __ldg(rj + 4 * fs);
-    float inter = (cur + prev + next + pprev + nnext) * sq;
-    float ctx = __ldg(context + o17);
-    prev = prev / d0;
-    next = next / d1;
-    pprev = pprev / d2;
-    nnext = nnext / d3;
-    float prev_b = cur + (prev + pprev), next_b = cur + (next + nnext);
-    float close_b = cur + (next + prev), far_b = cur + (nnext + pprev);
+    float v[2 * NP + 1];
+#pragma unroll
+    for (int f = 0; f < 2 * NP + 1; ++f) v[f] = __ldg(rj + f * fs);
+    const float cur = v[0];
+    float tot = cur;
+#pragma unroll
+    for (int f = 1; f < 2 * NP + 1; ++f) tot += v[f];
+    const float inter = tot * sq;
+    const float ctx = __ldg(context + o17);
+#pragma unroll
+    for (int f = 0; f < 2 * NP; ++f) v[f + 1] = v[f + 1] / den[f];
+    // v[2k-1] = prev_k', v[2k] = next_k'
+    float ps = v[1], ns = v[2];
+#pragma unroll
+    for (int k = 2; k <= NP; ++k) {
+      ps += v[2 * k - 1];
+      ns += v[2 * k];
+    }
+    const float prev_b = cur + ps, next_b = cur + ns;
+    const float close_b = cur + (v[2] + v[1]);
+    float far_b = cur;
+    if (NP >= 2) {
+      float fsum = v[4] + v[3];
+#pragma unroll
+      for (int k = 3; k <= NP; ++k) fsum += v[2 * k] + v[2 * k - 1];
+      far_b = cur + fsum;
+    }
     float v1[8] = {inter, ctx, prev_b, far_b, close_b, prev_b * sq, far_b * sq, close_b * sq};
     float v2[8] = {inter, ctx, next_b, close_b, far_b, next_b * sq, close_b * sq, far_b * sq};
 #pragma unroll
@@ -146,29 +178,60 @@ pyramid_conv_kernel(const float *__restrict__ s0, const float *__restrict__ s1,
 
 using namespace otp;
 
-extern "C" int otp_fusion_sum(const float *rough, int b, int j, int t, float *total_b, float *squeezed,
-                              otp_stream_t stream) {
+extern "C" int otp_fusion_sum_frames(const float *rough, int frames, int b, int j, int t, float *total_b,
+                                     float *squeezed, otp_stream_t stream) {
   OTP_REQUIRE(b >= 0 && j > 0 && t > 0 && b <= 65535);
+  if (frames != 3 && frames != 5 && frames != 7) {
+    set_error("otp_fusion_sum_frames: window of %d frames not built (3, 5 or 7)", frames);
+    return OTP_ERR_UNSUPPORTED;
+  }
   if (b == 0) return OTP_OK;
   OTP_REQUIRE(rough && total_b && squeezed);
-  LaunchScope ls(K_FUSION_SUM, (cudaStream_t)stream);
-  fusion_sum_kernel<<<dim3(ceil_div(t, kFuThreads), b), kFuThreads, 0, (cudaStream_t)stream>>>(
-      rough, b, j, t, total_b, squeezed);
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 grid(ceil_div(t, kFuThreads), b);
+  LaunchScope ls(K_FUSION_SUM, st);
+  if (frames == 3) fusion_sum_kernel<1><<<grid, kFuThreads, 0, st>>>(rough, b, j, t, total_b, squeezed);
+  else if (frames == 5) fusion_sum_kernel<2><<<grid, kFuThreads, 0, st>>>(rough, b, j, t, total_b, squeezed);
+  else fusion_sum_kernel<3><<<grid, kFuThreads, 0, st>>>(rough, b, j, t, total_b, squeezed);
   return check_launch("fusion_sum_kernel");
+}
+
+extern "C" int otp_fusion_sum(const float *rough, int b, int j, int t, float *total_b, float *squeezed,
+                              otp_stream_t stream) {
+  return otp_fusion_sum_frames(rough, 5, b, j, t, total_b, squeezed, stream);
+}
+
+extern "C" int otp_fusion_stack_frames(const float *rough, const int64_t *margin, const float *squeezed,
+                                       const float *context, const float *pe1, const float *pe2,
+                                       int pe_stride, int frames, int b, int j, int t, float *x1, float *x2,
+                                       float *intersection, float *prev_b, otp_stream_t stream) {
+  OTP_REQUIRE(b >= 0 && j > 0 && t > 0 && b <= 65535);
+  if (frames != 3 && frames != 5 && frames != 7) {
+    set_error("otp_fusion_stack_frames: window of %d frames not built (3, 5 or 7)", frames);
+    return OTP_ERR_UNSUPPORTED;
+  }
+  if (b == 0) return OTP_OK;
+  OTP_REQUIRE(rough && margin && squeezed && context && x1 && x2);
+  OTP_REQUIRE((!pe1 && !pe2) || pe_stride >= t);
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 grid(ceil_div(t, kFuThreads), b);
+  LaunchScope ls(K_FUSION_STACK, st);
+#define OTP_STACK(NP)                                                                                         \
+  fusion_stack_kernel<NP><<<grid, kFuThreads, 0, st>>>(rough, margin, squeezed, context, pe1, pe2, pe_stride, \
+                                                       b, j, t, x1, x2, intersection, prev_b)
+  if (frames == 3) OTP_STACK(1);
+  else if (frames == 5) OTP_STACK(2);
+  else OTP_STACK(3);
+#undef OTP_STACK
+  return check_launch("fusion_stack_kernel");
 }
 
 extern "C" int otp_fusion_stack(const float *rough, const int64_t *margin, const float *squeezed,
                                 const float *context, const float *pe1, const float *pe2, int pe_stride,
                                 int b, int j, int t, float *x1, float *x2, float *intersection,
                                 float *prev_b, otp_stream_t stream) {
-  OTP_REQUIRE(b >= 0 && j > 0 && t > 0 && b <= 65535);
-  if (b == 0) return OTP_OK;
-  OTP_REQUIRE(rough && margin && squeezed && context && x1 && x2);
-  OTP_REQUIRE((!pe1 && !pe2) || pe_stride >= t);
-  LaunchScope ls(K_FUSION_STACK, (cudaStream_t)stream);
-  fusion_stack_kernel<<<dim3(ceil_div(t, kFuThreads), b), kFuThreads, 0, (cudaStream_t)stream>>>(
-      rough, margin, squeezed, context, pe1, pe2, pe_stride, b, j, t, x1, x2, intersection, prev_b);
-  return check_launch("fusion_stack_kernel");
+  return otp_fusion_stack_frames(rough, margin, squeezed, context, pe1, pe2, pe_stride, 5, b, j, t, x1, x2,
+                                 intersection, prev_b, stream);
 }
 
 extern "C" int otp_add_pos_embd(const float *x, const float *pe, int pe_stride, float *y, int b, int c,

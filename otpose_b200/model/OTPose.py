@@ -172,9 +172,15 @@ class OTPose(nn.Module):
         rough = rough_heatmaps
         if rough.dtype != torch.float32 or not rough.is_contiguous():
             rough = rough.float().contiguous()
-        n5, j, h, w = rough.shape
-        assert n5 % 5 == 0 and j == self.num_joints and (h, w) == (self.pe_h, self.pe_w)
-        b, t, dev = n5 // 5, h * w, rough.device
+        nf, j, h, w = rough.shape
+        # frame window: 5 in the reference (`supplement = 5`, OTPose.py:188, 317-321); margin carries
+        # one column per supplementary frame, so (B, 2) / (B, 6) select the 3- / 7-frame extension
+        frames = margin.shape[1] + 1
+        if frames not in (3, 5, 7):
+            raise NotImplementedError(f"frame window of {frames} not built (3, 5 or 7)")
+        assert nf % frames == 0 and nf // frames == margin.shape[0], "rough_heatmaps / margin disagree on B"
+        assert j == self.num_joints and (h, w) == (self.pe_h, self.pe_w)
+        b, t, dev = nf // frames, h * w, rough.device
         if t % 4 != 0:
             raise ValueError("H*W must be divisible by 4 (two stride-2 branch levels are upsampled back)")
         margin = margin.to(device=dev, dtype=torch.int64).contiguous()
@@ -190,18 +196,19 @@ class OTPose(nn.Module):
             return out, rough_heatmaps, intersection, prev_b, ctx, squeezed.expand(b, j, h, w), total_b
         st = _lib.stream_ptr(dev)
         with torch.cuda.device(dev):
-            _lib.check(lib.otp_fusion_sum(_lib.dptr(rough), b, j, t, total_b.data_ptr(), squeezed.data_ptr(), st),
-                       "otp_fusion_sum")
+            _lib.check(lib.otp_fusion_sum_frames(_lib.dptr(rough), frames, b, j, t, total_b.data_ptr(),
+                                                 squeezed.data_ptr(), st), "otp_fusion_sum_frames")
             ctx = self.flow_encoder(total_b)[0]                                  # (B, J, T)
             x1 = torch.empty((b, c8, t), **f32)
             x2 = torch.empty((b, c8, t), **f32)
             pe1, ps1 = self.temporal_encoder1.pos_embd_for(t)
             pe2, ps2 = self.temporal_encoder2.pos_embd_for(t)
             assert ps1 == ps2
-            _lib.check(lib.otp_fusion_stack(
+            _lib.check(lib.otp_fusion_stack_frames(
                 _lib.dptr(rough), margin.data_ptr(), squeezed.data_ptr(), _lib.dptr(ctx),
-                _lib.dptr(pe1, allow_none=True), _lib.dptr(pe2, allow_none=True), ps1, b, j, t,
-                x1.data_ptr(), x2.data_ptr(), intersection.data_ptr(), prev_b.data_ptr(), st), "otp_fusion_stack")
+                _lib.dptr(pe1, allow_none=True), _lib.dptr(pe2, allow_none=True), ps1, frames, b, j, t,
+                x1.data_ptr(), x2.data_ptr(), intersection.data_ptr(), prev_b.data_ptr(), st),
+                "otp_fusion_stack_frames")
             cat = torch.empty((b, 3 * j, h, w), **f32)       # [final_layer1 | final_layer2 | def_heatmaps]
             for i, (enc, fl, xin) in enumerate(((self.temporal_encoder1, self.final_layer1, x1),
                                                 (self.temporal_encoder2, self.final_layer2, x2))):

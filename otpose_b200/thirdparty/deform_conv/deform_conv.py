@@ -28,10 +28,19 @@ def modulated_deform_conv(input, offset, mask, weight, bias=None, stride=1, padd
     """
     if not input.is_cuda:
         raise NotImplementedError
-    if any(t is not None and t.requires_grad and torch.is_grad_enabled()
-           for t in (input, offset, mask, weight, bias)):
-        raise NotImplementedError("modulated_deform_conv backward is a 'next' row (SURVEY.md 8 a12); "
-                                  "call under torch.no_grad()")
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad
+                                       for t in (input, offset, mask, weight, bias)):
+        if out is not None or accumulate or alpha != 1.0:
+            raise NotImplementedError("alpha/out/accumulate are inference-only extensions; "
+                                      "call under torch.no_grad() or drop them to train")
+        return ModulatedDeformConvFunction.apply(input, offset, mask, weight, bias, stride, padding, dilation,
+                                                 groups, deformable_groups)
+    return _mdcn_forward(input, offset, mask, weight, bias, stride, padding, dilation, groups,
+                         deformable_groups, alpha, out, accumulate)
+
+
+def _mdcn_forward(input, offset, mask, weight, bias, stride, padding, dilation, groups, deformable_groups,
+                  alpha=1.0, out=None, accumulate=False):
     b, c, h, w = input.shape
     cout, cin_g, kh, kw = weight.shape
     if c != cin_g * groups:
@@ -52,6 +61,48 @@ def modulated_deform_conv(input, offset, mask, weight, bias=None, stride=1, padd
             b, c, h, w, cout, kh, kw, stride, padding, dilation, groups, deformable_groups,
             float(alpha), int(accumulate), _lib.stream_ptr(input.device)), "otp_mdcn_forward")
     return out
+
+
+class ModulatedDeformConvFunction(torch.autograd.Function):
+    """Autograd wrapper with the reference's argument order (functions/deform_conv.py:109-180):
+    forward = ``otp_mdcn_forward``, backward = ``otp_mdcn_backward`` (one fused launch + a
+    fixed-order reduction; deterministic, unlike the reference's atomicAdd col2im)."""
+
+    @staticmethod
+    def forward(ctx, input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
+                deformable_groups=1):
+        ctx.conf = (stride, padding, dilation, groups, deformable_groups)
+        ctx.with_bias = bias is not None
+        input, offset, mask = input.contiguous(), offset.contiguous(), mask.contiguous()
+        weight = weight.contiguous()
+        ctx.save_for_backward(input, offset, mask, weight)
+        return _mdcn_forward(input.detach(), offset.detach(), mask.detach(), weight.detach(),
+                             bias.detach() if bias is not None else None, stride, padding, dilation, groups,
+                             deformable_groups)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_output):
+        if not grad_output.is_cuda:
+            raise NotImplementedError
+        input, offset, mask, weight = ctx.saved_tensors
+        stride, padding, dilation, groups, dg = ctx.conf
+        b, c, h, w = input.shape
+        cout, _, kh, kw = weight.shape
+        grad_output = grad_output.contiguous().float()
+        grad_input, grad_offset = torch.empty_like(input), torch.empty_like(offset)
+        grad_mask, grad_weight = torch.empty_like(mask), torch.empty_like(weight)
+        grad_bias = weight.new_empty(cout) if ctx.with_bias else None
+        lib = _lib.load()
+        nbytes = lib.otp_mdcn_backward_workspace_bytes(b, c, h, w, cout, kh, kw, stride, padding, dilation)
+        with torch.cuda.device(input.device):
+            ws = _lib.workspace.get(nbytes, input.device, "mdcn_bwd")
+            _lib.check(lib.otp_mdcn_backward(
+                _lib.dptr(input), _lib.dptr(offset), _lib.dptr(mask), _lib.dptr(weight), _lib.dptr(grad_output),
+                _lib.dptr(grad_input), _lib.dptr(grad_offset), _lib.dptr(grad_mask), _lib.dptr(grad_weight),
+                _lib.dptr(grad_bias, allow_none=True), b, c, h, w, cout, kh, kw, stride, padding, dilation,
+                groups, dg, ws.data_ptr(), nbytes, _lib.stream_ptr(input.device)), "otp_mdcn_backward")
+        return (grad_input, grad_offset, grad_mask, grad_weight, grad_bias, None, None, None, None, None)
 
 
 class ModulatedDeformConv(nn.Module):

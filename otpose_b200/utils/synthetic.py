@@ -111,10 +111,11 @@ def synth_rough_heatmaps(batch: int, joints: int, h: int, w: int, frames: int = 
     return torch.from_numpy(out.reshape(frames * batch, joints, h, w))
 
 
-def synth_margin(batch: int, seed: int = 1236) -> torch.Tensor:
-    """(batch, 4) int64 frame gaps in {0, 1, 2} (reference dataset/PoseTrackDataset.py:263-293)."""
+def synth_margin(batch: int, seed: int = 1236, frames: int = 5) -> torch.Tensor:
+    """(batch, frames-1) int64 frame gaps in {0, 1, 2} (reference dataset/PoseTrackDataset.py:263-293;
+    4 columns for the reference's 5-frame window)."""
     r = np.random.default_rng(seed)
-    return torch.from_numpy(r.integers(0, 3, (batch, 4)).astype(np.int64))
+    return torch.from_numpy(r.integers(0, 3, (batch, frames - 1)).astype(np.int64))
 
 
 def synth_center_scale(batch: int, seed: int = 1237):

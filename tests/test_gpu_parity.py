@@ -168,6 +168,83 @@ def test_mdcn_full_size_vs_torchvision_and_linearity():
     assert rel(acc, 1.5 * out1) < 1e-6
 
 
+def _mdcn_grads(fn, tensors, gout):
+    leaves = [t.detach().clone().requires_grad_(True) if t is not None else None for t in tensors]
+    out = fn(*leaves)
+    out.backward(gout.to(out.dtype).to(out.device))
+    return out.detach(), [t.grad for t in leaves if t is not None]
+
+
+@pytest.mark.parametrize("b,c,h,w,dg,stride,d,with_bias", [
+    (2, 17, 13, 11, 17, 1, 3, True),      # OTPose geometry, tiny map
+    (3, 17, 24, 18, 17, 1, 15, True),     # dilation larger than half the map: most taps out of range
+    (2, 6, 12, 10, 3, 2, 1, False),       # channels shared per deformable group, stride 2, no bias
+    (1, 17, 16, 12, 1, 1, 6, True),       # one deformable group over all channels
+])
+def test_mdcn_backward_vs_torchvision_float64(b, c, h, w, dg, stride, d, with_bias):
+    """a12: otp_mdcn_backward against torchvision's autograd in float64 on the CPU (the same
+    col2im / col2im_coord formulation as the reference kernels, deform_conv_cuda_kernel.cu:573-705)."""
+    from torchvision.ops import deform_conv2d
+    r = np.random.default_rng(100 + d + dg)
+    ho_, wo_ = (h + 2 * d - (2 * d + 1)) // stride + 1, (w + 2 * d - (2 * d + 1)) // stride + 1
+    x = torch.from_numpy(r.standard_normal((b, c, h, w)).astype(np.float32))
+    off = torch.from_numpy((r.standard_normal((b, dg * 18, ho_, wo_)) * 3).astype(np.float32))
+    msk = torch.from_numpy(r.standard_normal((b, dg * 9, ho_, wo_)).astype(np.float32))
+    wt = torch.from_numpy((r.standard_normal((17, c, 3, 3)) / 6).astype(np.float32))
+    bias = torch.from_numpy(r.standard_normal(17).astype(np.float32)) if with_bias else None
+    gout = torch.from_numpy(r.standard_normal((b, 17, ho_, wo_)).astype(np.float32))
+    tensors = (x, off, msk, wt, bias)
+    ref_out, ref = _mdcn_grads(
+        lambda x_, o_, m_, w_, b_: deform_conv2d(x_, o_, w_, b_, stride=stride, padding=d, dilation=d, mask=m_),
+        [t.double() if t is not None else None for t in tensors], gout)
+    out, got = _mdcn_grads(
+        lambda x_, o_, m_, w_, b_: modulated_deform_conv(x_, o_, m_, w_, b_, stride, d, d, 1, dg),
+        [t.cuda() if t is not None else None for t in tensors], gout)
+    assert rel(out, ref_out) < 1e-5
+    for name, g, e in zip(("x", "offset", "mask", "weight", "bias"), got, ref):
+        assert g is not None and g.shape == e.shape, name
+        assert rel(g, e) < 2e-5, name
+
+
+def test_mdcn_backward_full_size_deterministic_and_module_trains():
+    from torchvision.ops import deform_conv2d
+    r = np.random.default_rng(8)
+    b, d = 4, 9
+    x = cuda(r.standard_normal((b, 17, 96, 72)).astype(np.float32))
+    off = cuda((r.standard_normal((b, 306, 96, 72)) * 3).astype(np.float32))
+    msk = cuda(r.standard_normal((b, 153, 96, 72)).astype(np.float32))
+    gout = cuda(r.standard_normal((b, 17, 96, 72)).astype(np.float32))
+    m = ModulatedDeformConv(17, 17, 3, padding=d, dilation=d, deformable_groups=17).cuda()
+    with torch.no_grad():
+        m.bias.copy_(cuda(r.standard_normal(17).astype(np.float32)))
+    runs = []
+    for _ in range(2):
+        _, g = _mdcn_grads(lambda x_, o_, m_, w_, b_: modulated_deform_conv(x_, o_, m_, w_, b_, 1, d, d, 1, 17),
+                           (x, off, msk, m.weight, m.bias), gout)
+        runs.append(g)
+    # fixed-point scatter + fixed-order reductions: bit-identical from run to run
+    for a, c in zip(*runs):
+        assert torch.equal(a, c)
+    _, ref = _mdcn_grads(
+        lambda x_, o_, m_, w_, b_: deform_conv2d(x_, o_, w_, b_, stride=1, padding=d, dilation=d, mask=m_),
+        (x, off, msk, m.weight, m.bias), gout)
+    for name, g, e in zip(("x", "offset", "mask", "weight", "bias"), runs[0], ref):
+        assert rel(g, e) < 1e-4, name
+    # the module trains: one SGD step on a quadratic loss lowers it
+    opt = torch.optim.SGD(m.parameters(), lr=1e-3)
+    losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        loss = (m(x, off, msk) - gout).pow(2).mean()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert losses[2] < losses[1] < losses[0]
+    # inference-only extensions refuse to record a graph
+    with pytest.raises(NotImplementedError):
+        modulated_deform_conv(x, off, msk, m.weight, m.bias, 1, d, d, 1, 17, alpha=0.2)
+
+
 @pytest.mark.parametrize("fmt,tol", [("fp16", 3e-3), ("bf16", 2e-2)])
 @pytest.mark.parametrize("b,h,w,d", [(2, 96, 72, 3), (1, 96, 72, 15), (3, 13, 11, 6), (150, 16, 12, 9)])
 def test_fused_offset_mask_dcn_vs_unfused(b, h, w, d, fmt, tol):
@@ -233,6 +310,42 @@ def test_fusion_prologue_vs_oracle():
     assert rel(x1, e1) < 1e-6 and rel(x2, e2) < 1e-6
     assert rel(inter.view(b, j, h, w), f["intersection"]) < 1e-6
     assert rel(prev_b.view(b, j, h, w), f["prev_b"]) < 1e-6
+
+
+@pytest.mark.parametrize("frames", [3, 5, 7])
+def test_fusion_prologue_frame_window_vs_oracle(frames):
+    """BASELINE config 5 (T = 3 / 5 / 7): the windowed prologue against the generalised oracle,
+    whose 5-frame instance is the reference expression (tests/test_oracle.py)."""
+    b, j, h, w = 4, 17, 12, 8
+    t = h * w
+    rough = syn.synth_rough_heatmaps(b, j, h, w, frames=frames, seed=40 + frames)
+    margin = syn.synth_margin(b, seed=41, frames=frames)
+    f = ho.fusion_prologue_frames(rough, margin)
+    lib = _lib.load()
+    rg = rough.cuda()
+    total_b, sq = torch.empty(b, j, t).cuda(), torch.empty(b, t).cuda()
+    _lib.check(lib.otp_fusion_sum_frames(rg.data_ptr(), frames, b, j, t, total_b.data_ptr(), sq.data_ptr(), None))
+    assert torch.equal(total_b.cpu().view(b, j, h, w), f["total_b"])
+    ctx = torch.randn(b, j, t).cuda()
+    x1, x2 = torch.empty(b, 8 * j, t).cuda(), torch.empty(b, 8 * j, t).cuda()
+    inter, prev_b = torch.empty(b, j, t).cuda(), torch.empty(b, j, t).cuda()
+    _lib.check(lib.otp_fusion_stack_frames(rg.data_ptr(), margin.cuda().data_ptr(), sq.data_ptr(), ctx.data_ptr(),
+                                           None, None, 0, frames, b, j, t, x1.data_ptr(), x2.data_ptr(),
+                                           inter.data_ptr(), prev_b.data_ptr(), None))
+    c = ctx.cpu().view(b, j, h, w)
+    e1 = torch.stack((f["intersection"], c, f["prev_b"], f["far_b"], f["close_b"], f["prev_int"], f["far_int"],
+                      f["close_int"]), dim=2).flatten(1, 2).flatten(2)
+    e2 = torch.stack((f["intersection"], c, f["next_b"], f["close_b"], f["far_b"], f["next_int"], f["close_int"],
+                      f["far_int"]), dim=2).flatten(1, 2).flatten(2)
+    assert rel(x1, e1) < 1e-6 and rel(x2, e2) < 1e-6
+    assert torch.equal(prev_b.cpu().view(b, j, h, w), f["prev_b"])
+    if frames == 5:   # the 5-frame window IS otp_fusion_stack
+        y1, y2 = torch.empty_like(x1), torch.empty_like(x2)
+        _lib.check(lib.otp_fusion_stack(rg.data_ptr(), margin.cuda().data_ptr(), sq.data_ptr(), ctx.data_ptr(),
+                                        None, None, 0, b, j, t, y1.data_ptr(), y2.data_ptr(), None, None, None))
+        assert torch.equal(x1, y1) and torch.equal(x2, y2)
+    with pytest.raises(NotImplementedError):
+        _lib.check(lib.otp_fusion_sum_frames(rg.data_ptr(), 4, b, j, t, total_b.data_ptr(), sq.data_ptr(), None))
 
 
 # ----------------------------------------------------------------- a2-a5 encoders
@@ -381,6 +494,26 @@ def test_head_full_size_vs_oracle(precision):
     if precision == "fp32":
         ridx = ho.final_preds_full(ref[0].numpy(), center, scale)[0]
         assert np.array_equal(got["idx"].cpu().numpy(), ridx)
+
+
+@pytest.mark.parametrize("frames,precision", [(3, "fp16"), (5, "fp32"), (5, "fp16"), (7, "fp16")])
+def test_head_config5_window_sweep_128x96(frames, precision):
+    """BASELINE config 5: 512x384 input -> 128x96 heat maps (T = 12,288 tokens, max_len follows),
+    frame window 3 / 5 / 7.  frames != 5 is an extension: parity is against the generalised
+    oracle only (the reference hard-codes 5 frames)."""
+    b, h, w = 1, 128, 96
+    model, sd = build_head(h, w, precision)
+    rough = syn.synth_rough_heatmaps(b, 17, h, w, frames=frames, seed=77)
+    margin = syn.synth_margin(b, seed=78, frames=frames)
+    ref = ho.head_forward(sd, rough, margin)
+    outs = model.forward_head(rough.cuda(), margin.cuda())
+    for n, o, r in zip(NAMES, outs, ref):
+        if n == "rough_heatmaps":
+            continue
+        assert rel(o, r) < TOL[precision], n
+    center, scale = syn.synth_center_scale(b)
+    got = hm_mod.final_preds_cuda(outs[0], cuda(center), cuda(scale))
+    assert np.array_equal(got["idx"].cpu().numpy(), ho.final_preds_full(outs[0].cpu().numpy(), center, scale)[0])
 
 
 def test_bf16_operand_variant_documented_accuracy():

@@ -140,3 +140,31 @@ def test_scramble_formula():
             for s in range(t):
                 f = r_ * t + s
                 assert out2[0, h * hs + r_, s] == o[0, h, f % hs, f // hs]
+
+
+def test_frame_window_prologue_reduces_to_the_reference_at_5_frames():
+    """BASELINE config 5: the generalised (3/5/7-frame) prologue is a definition, pinned by
+    requiring its 5-frame instance to equal the line-for-line restatement of
+    model/OTPose.py:320-354 bit for bit."""
+    rough = syn.synth_rough_heatmaps(3, 17, 12, 8, seed=4)
+    margin = syn.synth_margin(3, seed=8)
+    a, b = ho.fusion_prologue(rough, margin), ho.fusion_prologue_frames(rough, margin)
+    assert a.keys() == b.keys()
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    # 3 frames: no far pair, so far_b is the current frame alone
+    r3 = syn.synth_rough_heatmaps(2, 17, 12, 8, frames=3, seed=5)
+    m3 = syn.synth_margin(2, seed=9, frames=3)
+    f3 = ho.fusion_prologue_frames(r3, m3)
+    cur, prev, nxt = r3.split(2, dim=0)
+    assert torch.equal(f3["far_b"], cur)
+    assert torch.equal(f3["total_b"], cur + prev + nxt)
+    assert torch.equal(f3["prev_b"], cur + prev / (m3[:, 0] + 1)[:, None, None, None])
+    # 7 frames: every supplementary frame contributes to total_b; far_b holds pairs 2 and 3
+    r7 = syn.synth_rough_heatmaps(2, 17, 12, 8, frames=7, seed=6)
+    m7 = torch.zeros(2, 6, dtype=torch.int64)
+    f7 = ho.fusion_prologue_frames(r7, m7)
+    fr = r7.split(2, dim=0)
+    assert relmax(f7["total_b"], sum(fr)) < 1e-6
+    assert relmax(f7["far_b"], fr[0] + fr[3] + fr[4] + fr[5] + fr[6]) < 1e-6
+    assert relmax(f7["prev_b"], fr[0] + fr[1] + fr[3] + fr[5]) < 1e-6
