@@ -218,6 +218,16 @@ int otp_offset_mask_dcn_forward(const void *packed, const float *trans, const fl
                                 int accumulate, int precision, otp_stream_t stream);
 
 /* ---------------------------------------------------------------------------
+ * Phase trace of the tensor-core block kernels (no reference counterpart; used
+ * to write profiles/): while enabled, CTA 0 of tc_back records
+ * (clock64 << 8 | event id) for one epilogue thread (row 0) and the control
+ * thread (row 1) into a 2 x 2048 device array; otp_debug_trace_read copies it
+ * to the host array `out` of n >= 4096 entries (synchronises the device).
+ * ------------------------------------------------------------------------- */
+int otp_debug_trace(int on);
+int otp_debug_trace_read(unsigned long long *out, int n);
+
+/* ---------------------------------------------------------------------------
  * Self-test of the tcgen05 / TMEM plumbing (no reference counterpart): one CTA
  * computes D[128,n] (fp32, row-major) = A . B^T over `ksteps` K=16 steps from
  * caller-built bf16 shared-memory operand images and explicit UMMA descriptor

@@ -7,6 +7,8 @@ int block_forward_simt(const void *packed, const float *x, float *y, int b, int 
                        void *ws, cudaStream_t st);
 // tcgen05 path (block_tc.cu)
 bool block_tc_built();
+void block_tc_trace(int on);
+int block_tc_trace_read(unsigned long long *out, int n);
 size_t block_tc_packed_bytes(int c);
 int block_tc_pack(const otp_block_params *p, int c, void *packed_tc, cudaStream_t st);
 size_t block_tc_workspace_bytes(int b, int c, int t, int stride);
@@ -27,6 +29,15 @@ static size_t fp32_pack_bytes(int c) { return align_up(block_pack_layout(c).tota
 using namespace otp;
 
 extern "C" int otp_has_tensor_core_path(void) { return block_tc_built() ? 1 : 0; }
+
+extern "C" int otp_debug_trace(int on) {
+  block_tc_trace(on);
+  return OTP_OK;
+}
+extern "C" int otp_debug_trace_read(unsigned long long *out, int n) {
+  OTP_REQUIRE(out != nullptr);
+  return block_tc_trace_read(out, n);
+}
 
 extern "C" size_t otp_block_packed_bytes(int c, int n_head) {
   if (check_shape(c, n_head) != OTP_OK) return 0;

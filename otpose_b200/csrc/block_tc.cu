@@ -39,7 +39,6 @@ constexpr int kC = 136, kHS = 68, kKP = 144;
 constexpr int kTM = 128;        // tokens per tile == UMMA M
 constexpr int kTcThreads = 384;
 constexpr int kApplyThreads = 256;
-constexpr int kBackThreads = 256;   // two CTAs per SM
 constexpr uint32_t kCS = 128;                 // byte stride between 8-element K chunks
 constexpr uint32_t kRS144 = (kKP / 8) * 128;  // byte stride between 8-row groups, K = 144
 constexpr uint32_t kTile144 = (kTM / 8) * kRS144;  // 36864  [128][144]
@@ -559,287 +558,8 @@ tc_apply_kernel(const uint8_t *__restrict__ vn_img, const uint8_t *__restrict__ 
 }
 
 // ------------------------------------------------------------------ tc_back
-// Two CTAs per SM (256 threads, <= 128 registers, ~109 KB shared memory, 256 TMEM columns each)
-// so that one CTA's tensor-core round trips / barriers overlap the other's CUDA-core epilogues.
-// Thread (q4, lane, half): token = 32*q4 + lane, 72 of the 144 accumulator columns.
-// u (the residual stream after attention) is parked in the output buffer in global memory
-// (an L2 round trip) instead of living in registers across the MLP, which is what lets two
-// tiles be in flight per SM.
-struct BackVec {
-  float bp[kKP], sa[kKP], b2[kKP], sm[kKP];
-  float b1p[kHidPad];
-  float part[2][2][kTM];
-};
-
-template <bool F16>
-__global__ void __launch_bounds__(kBackThreads, 2)
-tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__restrict__ b1p,
-               const float *__restrict__ x, const unsigned short *__restrict__ obuf, float *__restrict__ y,
-               int B, int T, int Tout, int stride, int tiles) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t *a = smem;                    // out2 tile, then LN2(u)
-  uint8_t *hbuf = a + kTile144;         // GELU(hidden chunk)
-  uint8_t *w1b = hbuf + kHTile;         // 2 x W1 chunk | the whole ring also holds Wp during the proj phase
-  uint8_t *w2b = w1b + 2 * kW1c;        // 2 x W2 chunk
-  BackVec *V = reinterpret_cast<BackVec *>(w2b + 2 * kW2c);
-  __shared__ uint64_t bar;
-  __shared__ uint32_t tmem_slot;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q4 = warp & 3, half = warp >> 2;
-  const int tok = q4 * 32 + lane;
-  constexpr TcPack L = tc_pack_layout();
-  static_assert(2 * kW1c + 2 * kW2c >= kW144, "Wp must fit the weight ring");
-
-  for (int n = threadIdx.x; n < kKP; n += kBackThreads) {
-    V->bp[n] = P.bp[n];
-    V->sa[n] = P.sa[n];
-    V->b2[n] = P.b2[n];
-    V->sm[n] = P.sm[n];
-  }
-  for (int n = threadIdx.x; n < kHidPad; n += kBackThreads) V->b1p[n] = b1p[n];
-  if (threadIdx.x == 0) {
-    mbar_init(&bar, 1);
-    fence_mbar_init();
-  }
-  if (warp == 0) tmem_alloc(&tmem_slot, 256);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tm = tmem_slot;
-  const uint32_t t_y = tm;                           // y accumulator; the proj accumulator before that
-  const uint32_t t_h[2] = {tm + 144, tm + 192};      // hidden chunk accumulators (N = 48), double-buffered
-  constexpr uint32_t kFmt = F16 ? 0u : 1u;
-  const uint32_t idesc144 = make_idesc_16(kKP, false, false, kFmt);
-  const uint32_t idescH = make_idesc_16(kNH, false, false, kFmt);
-  uint32_t ph = 0;
-  const int col_lo = half * 72;
-
-  auto issue_mma1 = [&](int j) {   // hidden chunk j: D_h[j&1] = LN2(u) . W1_j^T
-    const uint32_t aa = smem_u32(a), w1 = smem_u32(w1b + (j & 1) * kW1c);
-#pragma unroll
-    for (int s = 0; s < kKP / 16; ++s)
-      umma_bf16(t_h[j & 1], make_desc(aa + s * 2 * kCS, kCS, kRS144), make_desc(w1 + s * 2 * kCS, kCS, kRS144),
-                idescH, s > 0);
-  };
-
-  for (int g = blockIdx.x; g < B * tiles; g += gridDim.x) {
-    const int b = g / tiles, tile = g % tiles;
-    const int t0 = tile * kTM, nvalid = min(kTM, Tout - t0);
-    const bool live = tok < nvalid;
-    const int tt = t0 + tok;
-    cp_async_block(w1b, tcw + L.wp, kW144, kBackThreads);   // Wp into the (idle) weight ring
-    cp_async_commit();
-    // ---- the (nh, T', hs) 16-bit buffer re-read as (C, T'): A tile [token][channel];
-    //      loads are issued in batches of 24 before their first use ----
-    {
-      const unsigned short *ob = obuf + (size_t)b * kC * Tout + tt;
-      uint8_t *dst = a + cm_offset(tok, col_lo, kRS144, kCS);
-#pragma unroll
-      for (int part = 0; part < 3; ++part) {
-        unsigned short ov[24];
-#pragma unroll
-        for (int i = 0; i < 24; ++i) {
-          const int c = col_lo + part * 24 + i;
-          ov[i] = (live && c < kC) ? __ldg(ob + (size_t)c * Tout) : (unsigned short)0;
-        }
-#pragma unroll
-        for (int gg = 0; gg < 3; ++gg) {
-          uint4 w4;
-          w4.x = (uint32_t)ov[gg * 8 + 0] | ((uint32_t)ov[gg * 8 + 1] << 16);
-          w4.y = (uint32_t)ov[gg * 8 + 2] | ((uint32_t)ov[gg * 8 + 3] << 16);
-          w4.z = (uint32_t)ov[gg * 8 + 4] | ((uint32_t)ov[gg * 8 + 5] << 16);
-          w4.w = (uint32_t)ov[gg * 8 + 6] | ((uint32_t)ov[gg * 8 + 7] << 16);
-          *reinterpret_cast<uint4 *>(dst + (part * 3 + gg) * kCS) = w4;
-        }
-      }
-    }
-    cp_async_wait<0>();
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      tc_fence_after();
-      const uint32_t aa = smem_u32(a), ww = smem_u32(w1b);
-#pragma unroll
-      for (int s = 0; s < kKP / 16; ++s)
-        umma_bf16(t_y, make_desc(aa + s * 2 * kCS, kCS, kRS144), make_desc(ww + s * 2 * kCS, kCS, kRS144), idesc144,
-                  s > 0);
-      umma_commit(&bar);
-    }
-    // ---- skip path pool_skip(x) while the proj UMMA runs ----
-    float u[72];
-    {
-      const float *xb = x + (size_t)b * kC * T;
-#pragma unroll
-      for (int i = 0; i < 72; ++i) {
-        const int n = col_lo + i;
-        float skip = 0.f;
-        if (n < kC && live) {
-          const float *xr = xb + (size_t)n * T;
-          if (stride == 1) {
-            skip = __ldg(xr + tt);
-          } else {   // MaxPool1d(3, 2, 1)
-            const int c0 = 2 * tt;
-            skip = __ldg(xr + c0);
-            if (c0 - 1 >= 0) skip = fmaxf(skip, __ldg(xr + c0 - 1));
-            if (c0 + 1 < T) skip = fmaxf(skip, __ldg(xr + c0 + 1));
-          }
-        }
-        u[i] = skip;
-      }
-    }
-    mbar_wait(&bar, ph);
-    ph ^= 1;
-    tc_fence_after();
-    // the ring is free again: weight chunks {W1_0} and {W1_1, W2_0} stream in under the epilogue
-    cp_async_block(w1b, tcw + L.w1, kW1c, kBackThreads);
-    cp_async_commit();
-    cp_async_block(w1b + kW1c, tcw + L.w1 + kW1c, kW1c, kBackThreads);
-    cp_async_block(w2b, tcw + L.w2, kW2c, kBackThreads);
-    cp_async_commit();
-    // ---- u = skip(x) + s_a * (proj + b_p): parked in y (global), LN2 statistics from registers ----
-    {
-      float *yb = y + (size_t)b * kC * Tout + tt;
-      float s = 0.f;
-#pragma unroll
-      for (int gg = 0; gg < 9; ++gg) {
-        float v[8];
-        tmem_ld8(tcol(t_y, q4, col_lo + gg * 8), v);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int n = col_lo + gg * 8 + e;
-          const float val = (n < kC && live) ? fmaf(V->sa[n], v[e] + V->bp[n], u[gg * 8 + e]) : 0.f;
-          u[gg * 8 + e] = val;
-          s += val;
-          if (n < kC && live) yb[(size_t)n * Tout] = val;
-        }
-      }
-      V->part[0][half][tok] = s;
-    }
-    __syncthreads();
-    const float mu = (V->part[0][0][tok] + V->part[0][1][tok]) * (1.0f / kC);
-    {
-      float s = 0.f;
-#pragma unroll
-      for (int i = 0; i < 72; ++i) {
-        const float d = (col_lo + i < kC) ? u[i] - mu : 0.f;
-        s = fmaf(d, d, s);
-      }
-      V->part[1][half][tok] = s;
-    }
-    __syncthreads();
-    {
-      const float rstd = 1.0f / sqrtf((V->part[1][0][tok] + V->part[1][1][tok]) * (1.0f / kC) + 1e-5f);
-      uint8_t *dst = a + cm_offset(tok, col_lo, kRS144, kCS);
-#pragma unroll
-      for (int gg = 0; gg < 9; ++gg) {
-        float h8[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) h8[e] = (col_lo + gg * 8 + e < kC) ? (u[gg * 8 + e] - mu) * rstd : 0.f;
-        *reinterpret_cast<uint4 *>(dst + gg * kCS) = pack16x8<F16>(h8);
-      }
-    }
-    // ---- MLP: W1 chunk j+1 runs on the tensor cores while the CUDA cores do GELU(chunk j) ----
-    cp_async_wait<1>();   // {W1_0}
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      tc_fence_after();
-      issue_mma1(0);
-      umma_commit(&bar);
-    }
-#pragma unroll 1
-    for (int j = 0; j < kNChunk; ++j) {
-      mbar_wait(&bar, ph);   // W1 chunk j done (and W2 chunk j-1: hbuf and its weight buffer are free)
-      ph ^= 1;
-      tc_fence_after();
-      cp_async_wait<0>();    // {W1_{j+1}, W2_j}
-      fence_async_smem();
-      tc_fence_before();
-      __syncthreads();
-      if (threadIdx.x == 0 && j + 1 < kNChunk) {
-        tc_fence_after();
-        issue_mma1(j + 1);
-      }
-      if (j + 2 < kNChunk) cp_async_block(w1b + (j & 1) * kW1c, tcw + L.w1 + (size_t)(j + 2) * kW1c, kW1c, kBackThreads);
-      if (j + 1 < kNChunk)
-        cp_async_block(w2b + ((j + 1) & 1) * kW2c, tcw + L.w2 + (size_t)(j + 1) * kW2c, kW2c, kBackThreads);
-      cp_async_commit();
-      // GELU(hidden chunk j) -> 16-bit H tile: 24 columns per thread
-      {
-        const int col = half * 24;
-        const uint32_t ta = tcol(t_h[j & 1], q4, col);
-        uint32_t r0[16], r1[8];
-        tmem_ld16_nw(ta, r0);
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]), "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]),
-                       "=r"(r1[7])
-                     : "r"(ta + 16)
-                     : "memory");
-        tmem_wait_ld();
-        reg_fence16(r0);
-        asm volatile("" : "+r"(r1[0]), "+r"(r1[1]), "+r"(r1[2]), "+r"(r1[3]), "+r"(r1[4]), "+r"(r1[5]), "+r"(r1[6]),
-                     "+r"(r1[7])::"memory");
-        uint8_t *dst = hbuf + cm_offset(tok, col, kRS96, kCS);
-        const float *bb = V->b1p + j * kNH + col;
-#pragma unroll
-        for (int gg = 0; gg < 3; ++gg) {
-          float v[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e)
-            v[e] = __uint_as_float(gg < 2 ? r0[gg * 8 + e] : r1[e]) + bb[gg * 8 + e];
-          uint4 w4;
-          w4.x = gelu_pair<F16>(v[0], v[1]);
-          w4.y = gelu_pair<F16>(v[2], v[3]);
-          w4.z = gelu_pair<F16>(v[4], v[5]);
-          w4.w = gelu_pair<F16>(v[6], v[7]);
-          *reinterpret_cast<uint4 *>(dst + gg * kCS) = w4;
-        }
-      }
-      fence_async_smem();
-      tc_fence_before();
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        tc_fence_after();
-        const uint32_t hh = smem_u32(hbuf), w2 = smem_u32(w2b + (j & 1) * kW2c);
-#pragma unroll
-        for (int s = 0; s < kNH / 16; ++s)
-          umma_bf16(t_y, make_desc(hh + s * 2 * kCS, kCS, kRS96), make_desc(w2 + s * 2 * kCS, kCS, kRS96), idesc144,
-                    (j > 0 || s > 0));
-        umma_commit(&bar);   // completes when W1 chunk j+1 (issued above) and this W2 chunk are both done
-      }
-    }
-    mbar_wait(&bar, ph);
-    ph ^= 1;
-    tc_fence_after();
-    // ---- y = u + s_m * (mlp + b_2), u read back from the output buffer ----
-    {
-      float *yb = y + (size_t)b * kC * Tout + tt;
-#pragma unroll 1
-      for (int gg = 0; gg < 9; ++gg) {
-        float v[8], uu[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int n = col_lo + gg * 8 + e;
-          uu[e] = (n < kC && live) ? yb[(size_t)n * Tout] : 0.f;
-        }
-        tmem_ld8(tcol(t_y, q4, col_lo + gg * 8), v);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int n = col_lo + gg * 8 + e;
-          if (n < kC && live) yb[(size_t)n * Tout] = fmaf(V->sm[n], v[e] + V->b2[n], uu[e]);
-        }
-      }
-    }
-    cp_async_wait<0>();
-    tc_fence_before();
-    __syncthreads();   // TMEM / smem reuse by the next tile
-    tc_fence_after();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tm, 256);
-}
+int g_trace_on = 0;   // otp_debug_trace
+#include "block_tc_back.cuh"
 
 // ------------------------------------------------------------------ weight packing
 // operand image of src[row0 + r][col0 + k] * colscale[col0 + k]   (zero padded)
@@ -856,6 +576,15 @@ __global__ void pack_image_kernel(const float *__restrict__ src, int ld, int row
     if (colscale) v *= colscale[col0 + k];
   }
   *reinterpret_cast<unsigned short *>(dst + cm_offset(r, k, (cols_pad / 8) * 128, 128)) = to16<F16>(v);
+}
+// column `col` of an operand image <- bias[row0 + r] (r < rows_valid): the bias rides in the MMA
+// against a ones column of the activation tile
+template <bool F16>
+__global__ void pack_bias_col_kernel(const float *__restrict__ bias, int row0, int rows_valid, uint8_t *__restrict__ dst,
+                                     int cols_pad, int col) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < rows_valid)
+    *reinterpret_cast<unsigned short *>(dst + cm_offset(r, col, (cols_pad / 8) * 128, 128)) = to16<F16>(bias[row0 + r]);
 }
 // out[n] = bias[n] + sum_c w[n][c] * lnb[c]  (n < rows), 0 for the padding
 __global__ void fold_bias_kernel(const float *__restrict__ w, const float *__restrict__ bias,
@@ -886,7 +615,7 @@ void pack_image(bool f16, const float *src, int ld, int row0, int col0, int rv, 
 
 constexpr size_t kFrontSmem = (size_t)kC * kXLD * 4 + 2 * kTile144 + kW144 + sizeof(FrontVec);
 constexpr size_t kApplySmem = (size_t)kTile144 + kW144;
-constexpr size_t kBackSmem = (size_t)kTile144 + kHTile + 2 * kW1c + 2 * kW2c + sizeof(BackVec);
+constexpr size_t kBackSmem = (size_t)kTile144 + 2 * kHTile + kBackSlots * kW1c + sizeof(BackVec);
 static_assert(kFrontSmem <= 226 * 1024, "tc_front shared memory");
 static_assert(2 * (kBackSmem + 1024) <= 227 * 1024, "tc_back: two CTAs per SM");
 
@@ -902,7 +631,6 @@ int forward_tc_t(const void *packed_fp32, const void *packed_tc, const float *x,
   const float *bvp = reinterpret_cast<const float *>(base + L.bvp);
   const float *bqp = reinterpret_cast<const float *>(base + L.bqp);
   const float *bkp = reinterpret_cast<const float *>(base + L.bkp);
-  const float *b1p = reinterpret_cast<const float *>(base + L.b1p);
   uint8_t *ws = static_cast<uint8_t *>(ws_tc);
   float *gram = reinterpret_cast<float *>(ws + W.gram_part);
   float *beff = reinterpret_cast<float *>(ws + W.beff);
@@ -913,7 +641,8 @@ int forward_tc_t(const void *packed_fp32, const void *packed_tc, const float *x,
   if (!attr_done) {
     cudaFuncSetAttribute(tc_front_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFrontSmem);
     cudaFuncSetAttribute(tc_apply_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kApplySmem);
-    cudaFuncSetAttribute(tc_back_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBackSmem);
+    cudaFuncSetAttribute(tc_back_kernel<F16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBackSmem);
+    cudaFuncSetAttribute(tc_back_kernel<F16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBackSmem);
     attr_done = true;
   }
   {
@@ -934,8 +663,11 @@ int forward_tc_t(const void *packed_fp32, const void *packed_tc, const float *x,
   {
     LaunchScope ls(K_TC_BACK, st);
     const int total = b * W.tiles;
-    tc_back_kernel<F16><<<min(total, 2 * num_sms()), kBackThreads, kBackSmem, st>>>(P, tcw, b1p, x, obuf, y, b, t, W.tout,
-                                                                             stride, W.tiles);
+    const int grid = min(total, 2 * num_sms());
+    if (stride == 1)
+      tc_back_kernel<F16, false><<<grid, kBackThreads, kBackSmem, st>>>(P, tcw, x, obuf, y, b, t, W.tout, W.tiles, g_trace_on);
+    else
+      tc_back_kernel<F16, true><<<grid, kBackThreads, kBackSmem, st>>>(P, tcw, x, obuf, y, b, t, W.tout, W.tiles, g_trace_on);
   }
   return check_launch("block_forward_tc");
 }
@@ -943,13 +675,24 @@ int forward_tc_t(const void *packed_fp32, const void *packed_tc, const float *x,
 
 bool block_tc_built() { return true; }
 
+void block_tc_trace(int on) { g_trace_on = on; }
+int block_tc_trace_read(unsigned long long *out, int n) {
+  if (n < 2 * kTraceLen) return OTP_ERR_ARG;
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_back_trace, sizeof(unsigned long long) * 2 * kTraceLen);
+  if (e != cudaSuccess) {
+    set_error("block_tc_trace_read: %s", cudaGetErrorString(e));
+    return OTP_ERR_CUDA;
+  }
+  return OTP_OK;
+}
+
 size_t block_tc_packed_bytes(int c) { return c == kC ? align_up(tc_pack_layout().total, 1024) : 0; }
 
 int block_tc_pack(const otp_block_params *p, int c, void *packed_tc, cudaStream_t st) {
   if (c != kC) return OTP_OK;
   constexpr TcPack L = tc_pack_layout();
   uint8_t *base = static_cast<uint8_t *>(packed_tc);
-  LaunchScope ls(K_PACK, st, 35);
+  LaunchScope ls(K_PACK, st, 61);
   for (int f = 0; f < 2; ++f) {
     uint8_t *d = base + f * L.img_bytes;
     // LN_q / LN_k / LN2 affine folded in: W' = W diag(g), b' = b + W beta (fp32 vectors below)
@@ -969,6 +712,20 @@ int block_tc_pack(const otp_block_params *p, int c, void *packed_tc, cudaStream_
   fold_bias_kernel<<<1, 256, 0, st>>>(p->k_w, p->k_b, p->k_norm_b, reinterpret_cast<float *>(base + L.bkp), kC, kC, kKP);
   fold_bias_kernel<<<ceil_div(kHidPad, 256), 256, 0, st>>>(p->mlp0_w, p->mlp0_b, p->ln2_b,
                                                            reinterpret_cast<float *>(base + L.b1p), 4 * kC, kC, kHidPad);
+  // biases folded into operand column 136 (tc_back): b_p into Wp, b_1 + W_1 beta_2 into the W1 chunks
+  const float *b1f = reinterpret_cast<const float *>(base + L.b1p);
+  for (int f = 0; f < 2; ++f) {
+    uint8_t *d = base + f * L.img_bytes;
+    if (f) {
+      pack_bias_col_kernel<true><<<1, 256, 0, st>>>(p->proj_b, 0, kC, d + L.wp, kKP, kC);
+      for (int j = 0; j < kNChunk; ++j)
+        pack_bias_col_kernel<true><<<1, 64, 0, st>>>(b1f, j * kNH, kNH, d + L.w1 + (size_t)j * kW1c, kKP, kC);
+    } else {
+      pack_bias_col_kernel<false><<<1, 256, 0, st>>>(p->proj_b, 0, kC, d + L.wp, kKP, kC);
+      for (int j = 0; j < kNChunk; ++j)
+        pack_bias_col_kernel<false><<<1, 64, 0, st>>>(b1f, j * kNH, kNH, d + L.w1 + (size_t)j * kW1c, kKP, kC);
+    }
+  }
   return check_launch("block_tc_pack");
 }
 
