@@ -220,11 +220,15 @@ int otp_offset_mask_dcn_forward(const void *packed, const float *trans, const fl
 /* ---------------------------------------------------------------------------
  * Phase trace of the tensor-core block kernels (no reference counterpart; used
  * to write profiles/): while enabled, CTA 0 of tc_back records
- * (clock64 << 8 | event id) for one epilogue thread (row 0) and the control
- * thread (row 1) into a 2 x 2048 device array; otp_debug_trace_read copies it
- * to the host array `out` of n >= 4096 entries (synchronises the device).
+ * (clock64 << 8 | event id) for epilogue warp 0 (row 0), the control warp
+ * (row 1) and epilogue warp 15 (row 2) into a 3 x 2048 device array;
+ * otp_debug_trace_read copies it to the host array `out` of n >= 6144 entries
+ * (synchronises the device).
  * ------------------------------------------------------------------------- */
 int otp_debug_trace(int on);
+/* UMMA rate probe: `ctas` CTAs each issue reps x ksteps M128 x n x K16 UMMAs; cycles_host gets
+ * 2 values per CTA: clock64 cycles of the issue loop, and of issue + completion. */
+int otp_debug_umma_rate(int n, int ksteps, int reps, int ctas, long long *cycles_host);
 int otp_debug_trace_read(unsigned long long *out, int n);
 
 /* ---------------------------------------------------------------------------

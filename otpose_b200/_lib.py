@@ -61,6 +61,7 @@ SIGNATURES = {
     "otp_offset_mask_pack": (i32, [vp, vp, i32, i32, vp, sz, vp]),
     "otp_offset_mask_dcn_forward": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, i32, vp]),
     "otp_debug_trace": (i32, [i32]),
+    "otp_debug_umma_rate": (i32, [i32, i32, i32, i32, C.POINTER(C.c_longlong)]),
     "otp_debug_trace_read": (i32, [C.POINTER(C.c_ulonglong), i32]),
     "otp_debug_umma_gemm": (i32, [vp, i32, vp, i32, vp, i32, i32] + [C.c_uint] * 8 + [i32, i32, i32, vp]),
 }

@@ -43,7 +43,7 @@ constexpr uint32_t kCS = 128;                 // byte stride between 8-element K
 constexpr uint32_t kRS144 = (kKP / 8) * 128;  // byte stride between 8-row groups, K = 144
 constexpr uint32_t kTile144 = (kTM / 8) * kRS144;  // 36864  [128][144]
 constexpr uint32_t kW144 = (kKP / 8) * kRS144;     // 41472  [144][144]
-constexpr int kNH = 48, kNChunk = 12, kHidPad = kNH * kNChunk;  // hidden 544 -> 576, 12 chunks of 48
+constexpr int kNH = 64, kNChunk = 9, kHidPad = kNH * kNChunk;  // hidden 544 -> 576, 9 chunks of 64
 constexpr uint32_t kRS96 = (kNH / 8) * 128;        // 768  (row-group stride of a K = 48 tile)
 constexpr uint32_t kW1c = (kNH / 8) * kRS144;      // 13824  [48][144]
 constexpr uint32_t kW2c = (kKP / 8) * kRS96;       // 13824  [144][48]
@@ -615,9 +615,9 @@ void pack_image(bool f16, const float *src, int ld, int row0, int col0, int rv, 
 
 constexpr size_t kFrontSmem = (size_t)kC * kXLD * 4 + 2 * kTile144 + kW144 + sizeof(FrontVec);
 constexpr size_t kApplySmem = (size_t)kTile144 + kW144;
-constexpr size_t kBackSmem = (size_t)kTile144 + 2 * kHTile + kBackSlots * kW1c + sizeof(BackVec);
+constexpr size_t kBackSmem = (size_t)2 * kTile144 + kW144 + kBackTH * kHTile + kBackSlots * kW1c + sizeof(BackVec);
 static_assert(kFrontSmem <= 226 * 1024, "tc_front shared memory");
-static_assert(2 * (kBackSmem + 1024) <= 227 * 1024, "tc_back: two CTAs per SM");
+static_assert(kBackSmem + 1024 <= 227 * 1024, "tc_back shared memory");
 
 template <bool F16>
 int forward_tc_t(const void *packed_fp32, const void *packed_tc, const float *x, float *y, int b, int t, int stride,
@@ -663,7 +663,7 @@ int forward_tc_t(const void *packed_fp32, const void *packed_tc, const float *x,
   {
     LaunchScope ls(K_TC_BACK, st);
     const int total = b * W.tiles;
-    const int grid = min(total, 2 * num_sms());
+    const int grid = min(total, num_sms());
     if (stride == 1)
       tc_back_kernel<F16, false><<<grid, kBackThreads, kBackSmem, st>>>(P, tcw, x, obuf, y, b, t, W.tout, W.tiles, g_trace_on);
     else
@@ -677,8 +677,8 @@ bool block_tc_built() { return true; }
 
 void block_tc_trace(int on) { g_trace_on = on; }
 int block_tc_trace_read(unsigned long long *out, int n) {
-  if (n < 2 * kTraceLen) return OTP_ERR_ARG;
-  cudaError_t e = cudaMemcpyFromSymbol(out, g_back_trace, sizeof(unsigned long long) * 2 * kTraceLen);
+  if (n < 3 * kTraceLen) return OTP_ERR_ARG;
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_back_trace, sizeof(unsigned long long) * 3 * kTraceLen);
   if (e != cudaSuccess) {
     set_error("block_tc_trace_read: %s", cudaGetErrorString(e));
     return OTP_ERR_CUDA;

@@ -56,20 +56,31 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (launch error) after ~2 s instead of hanging the GPU.
+// try_wait carries a suspend-time hint, so a waiting warp sleeps in hardware until the phase
+// completes instead of competing for issue slots with the warps it is waiting for.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
-  for (uint32_t spin = 0;; ++spin) {
-    uint32_t done;
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  if (done) return;
+  const long long t0 = clock64();
+  for (;;) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(100000u)
         : "memory");
     if (done) return;
-    if (spin > (1u << 22)) __trap();
+    if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
 

@@ -56,6 +56,61 @@ umma_selftest_kernel(const uint4 *__restrict__ a_img, int a_bytes, const uint4 *
   if (threadIdx.x < 32) tc::tmem_dealloc(tmem, 256);
 }
 
+
+// UMMA issue/execute rate probe: one warp per CTA issues `reps` x `ksteps` M128 x N x K16 UMMAs
+// (operands: zeroed shared memory, K-major) and measures clock64 from first issue to completion.
+__global__ void __launch_bounds__(128)
+umma_rate_kernel(int n, int ksteps, int reps, long long *__restrict__ cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const uint32_t rs = (uint32_t)ksteps * 2 * 128;            // row-group stride of a K = 16*ksteps tile
+  const uint32_t a_bytes = 16 * rs, b_bytes = (uint32_t)(n / 8) * rs;
+  for (uint32_t i = threadIdx.x; i < (a_bytes + b_bytes) / 16; i += 128)
+    reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::fence_mbar_init();
+  }
+  if (threadIdx.x < 32) tc::tmem_alloc(&tmem_slot, 256);
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  if (threadIdx.x < 32) {
+    const uint32_t tmem = tmem_slot, aa = tc::smem_u32(smem), bb = aa + a_bytes;
+    const uint32_t idesc = tc::make_idesc_bf16(n, false, false);
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r)
+      for (int s = 0; s < ksteps; ++s) {
+        const uint64_t ad = tc::make_desc(aa + s * 256, 128, rs), bd = tc::make_desc(bb + s * 256, 128, rs);
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\t"
+            "elect.sync _|q, 0xffffffff;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem), "l"(ad), "l"(bd), "r"(idesc), "r"((uint32_t)(s > 0))
+            : "memory");
+      }
+    const long long t1 = clock64();
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(tc::smem_u32(&bar))
+        : "memory");
+    tc::mbar_wait(&bar, 0);
+    const long long t2 = clock64();
+    if (threadIdx.x == 0) {
+      cycles[2 * blockIdx.x] = t1 - t0;       // issue
+      cycles[2 * blockIdx.x + 1] = t2 - t0;   // issue + drain
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tc::tmem_dealloc(tmem_slot, 256);
+}
+
 }  // namespace otp
 
 extern "C" int otp_debug_umma_gemm(const void *a_img, int a_bytes, const void *b_img, int b_bytes, float *d,
@@ -72,4 +127,22 @@ extern "C" int otp_debug_umma_gemm(const void *a_img, int a_bytes, const void *b
       static_cast<const uint4 *>(a_img), a_bytes, static_cast<const uint4 *>(b_img), b_bytes, d, n, ksteps, a_off,
       a_lbo, a_sbo, a_kstep, b_off, b_lbo, b_sbo, b_kstep, a_mn_major, b_mn_major, repeat);
   return otp::check_launch("umma_selftest_kernel");
+}
+
+extern "C" int otp_debug_umma_rate(int n, int ksteps, int reps, int ctas, long long *cycles_host) {
+  using namespace otp;
+  OTP_REQUIRE(n >= 16 && n <= 256 && n % 16 == 0 && ksteps >= 1 && ksteps <= 9 && reps >= 1 && ctas >= 1 &&
+              ctas <= 1024 && cycles_host != nullptr);
+  const size_t smem = (size_t)(16 + n / 8) * ksteps * 256;
+  cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  long long *dev = nullptr;
+  if (cudaMalloc(&dev, sizeof(long long) * 2 * ctas) != cudaSuccess) return OTP_ERR_CUDA;
+  umma_rate_kernel<<<ctas, 128, smem>>>(n, ksteps, reps, dev);
+  cudaError_t e = cudaMemcpy(cycles_host, dev, sizeof(long long) * 2 * ctas, cudaMemcpyDeviceToHost);
+  cudaFree(dev);
+  if (e != cudaSuccess) {
+    set_error("otp_debug_umma_rate: %s", cudaGetErrorString(e));
+    return OTP_ERR_CUDA;
+  }
+  return OTP_OK;
 }

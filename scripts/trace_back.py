@@ -31,10 +31,12 @@ with torch.no_grad():
     blk(x, precision="fp16")
     torch.cuda.synchronize()
     lib.otp_debug_trace(0)
-buf = (C.c_ulonglong * 4096)()
-_lib.check(lib.otp_debug_trace_read(buf, 4096), "trace_read")
-arr = np.frombuffer(buf, dtype=np.uint64).reshape(2, 2048)
-for role, name in enumerate(("epilogue warp 0", "control")):
+buf = (C.c_ulonglong * 6144)()
+_lib.check(lib.otp_debug_trace_read(buf, 6144), "trace_read")
+arr = np.frombuffer(buf, dtype=np.uint64).reshape(3, 2048)
+names = ("E0", "CT", "E15")
+per_role = []
+for role in range(3):
     ev = [(int(v) & 0xFF, int(v) >> 8) for v in arr[role] if v]
     tiles, cur = [], []
     for e, c in ev:
@@ -44,15 +46,12 @@ for role, name in enumerate(("epilogue warp 0", "control")):
         cur.append((e, c))
     if cur:
         tiles.append(cur)
-    print(f"== {name}: {len(tiles)} tiles, tile period (cycles):",
+    per_role.append(tiles)
+    print(f"== {names[role]}: {len(tiles)} tiles, tile period (cycles):",
           [tiles[i + 1][0][1] - tiles[i][0][1] for i in range(len(tiles) - 1)])
-    offs, durs = {}, {}
-    for tl in tiles[1:]:   # skip the cold first tile
-        t0 = tl[0][1]
-        for i, (e, c) in enumerate(tl):
-            offs.setdefault(e, []).append(c - t0)
-            if i:
-                durs.setdefault(e, []).append(c - tl[i - 1][1])
-    order = [e for e, _ in tiles[-1]]
-    print("event: offset / since-previous (median cycles)")
-    print("  ".join(f"{e}:{int(statistics.median(offs[e]))}/{int(statistics.median(durs.get(e, [0])))}" for e in order))
+# merged absolute timeline of one steady-state tile (clock64 is per SM: directly comparable)
+k = min(len(t) for t in per_role) // 2
+origin = per_role[1][k][0][1]
+merged = sorted((c - origin, names[r], e) for r in range(3) for e, c in per_role[r][k])
+print(f"-- tile #{k}: cycle offset from the control warp's tile start, role:event")
+print("  ".join(f"{c}:{n}:{e}" for c, n, e in merged))
