@@ -561,6 +561,9 @@ tc_apply_kernel(const uint8_t *__restrict__ vn_img, const uint8_t *__restrict__ 
 int g_trace_on = 0;   // otp_debug_trace
 #include "block_tc_back.cuh"
 
+// ------------------------------------------------------------------ tc_front, stride-1 blocks
+#include "block_tc_front.cuh"
+
 // ------------------------------------------------------------------ weight packing
 // operand image of src[row0 + r][col0 + k] * colscale[col0 + k]   (zero padded)
 template <bool F16>
@@ -640,6 +643,7 @@ int forward_tc_t(const void *packed_fp32, const void *packed_tc, const float *x,
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(tc_front_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFrontSmem);
+    cudaFuncSetAttribute(tc_front1_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFront1Smem);
     cudaFuncSetAttribute(tc_apply_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kApplySmem);
     cudaFuncSetAttribute(tc_back_kernel<F16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBackSmem);
     cudaFuncSetAttribute(tc_back_kernel<F16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBackSmem);
@@ -647,9 +651,13 @@ int forward_tc_t(const void *packed_fp32, const void *packed_tc, const float *x,
   }
   {
     LaunchScope ls(K_TC_FRONT, st);
-    tc_front_kernel<F16><<<dim3(W.nchunk, b), kTcThreads, kFrontSmem, st>>>(
-        P, tcw, bqp, bkp, x, gram, vn, t, W.tout, stride, W.tiles, W.tiles_per_chunk, W.nchunk,
-        1.0f / sqrtf((float)kHS));
+    if (stride == 1)
+      tc_front1_kernel<F16><<<dim3(W.nchunk, b), kFrThreads, kFront1Smem, st>>>(
+          P, tcw, bqp, bkp, x, gram, vn, t, W.tiles, W.tiles_per_chunk, W.nchunk, 1.0f / sqrtf((float)kHS));
+    else
+      tc_front_kernel<F16><<<dim3(W.nchunk, b), kTcThreads, kFrontSmem, st>>>(
+          P, tcw, bqp, bkp, x, gram, vn, t, W.tout, stride, W.tiles, W.tiles_per_chunk, W.nchunk,
+          1.0f / sqrtf((float)kHS));
   }
   {
     LaunchScope ls(K_BLOCK_FOLD, st);
