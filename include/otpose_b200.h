@@ -199,6 +199,19 @@ int otp_conv2d(const float *x, long long x_bstride, const float *x_add, long lon
                long long residual_bstride, float *y, long long y_bstride, int b, int cin, int h,
                int w, int cout, int k, int dilation, int relu, otp_stream_t stream);
 
+/* a7, 16-bit tensor-core variant of otp_conv2d (dilation 1, w % 8 == 0, <= 96 channels):
+ * implicit GEMM on tcgen05 over three pre-shifted 16-bit copies of the input rows (no im2col
+ * tile), fp32 accumulate / bias / residual / output.  `packed` = otp_conv2d_tc_pack of the
+ * (BatchNorm-folded) fp32 weight for the same precision (OTP_PREC_FP16 / OTP_PREC_BF16). */
+int otp_conv2d_tc_supported(int cin, int cout, int h, int w, int k); /* 1 if otp_conv2d_tc handles the shape */
+size_t otp_conv2d_tc_pack_bytes(int cin, int cout, int k);
+int otp_conv2d_tc_pack(const float *weight, int cin, int cout, int k, int precision, void *packed,
+                       size_t packed_bytes, otp_stream_t stream);
+int otp_conv2d_tc(const float *x, long long x_bstride, const float *x_add, long long x_add_bstride,
+                  const void *packed, const float *bias, const float *residual,
+                  long long residual_bstride, float *y, long long y_bstride, int b, int cin, int h,
+                  int w, int cout, int k, int relu, int precision, otp_stream_t stream);
+
 /* ---------------------------------------------------------------------------
  * a8 + a9 + a10 fused (tensor-core precisions only): for one dilation d,
  *   offsets = conv3x3_d(trans; w_off), masks = conv3x3_d(trans; w_msk),

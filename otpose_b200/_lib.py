@@ -57,6 +57,11 @@ SIGNATURES = {
     "otp_pyramid_conv1x1": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, vp, i64, vp]),
     "otp_conv2d": (i32, [vp, i64, vp, i64, vp, vp, vp, i64, vp, i64, i32, i32, i32, i32, i32, i32, i32,
                          i32, vp]),
+    "otp_conv2d_tc_supported": (i32, [i32, i32, i32, i32, i32]),
+    "otp_conv2d_tc_pack_bytes": (sz, [i32, i32, i32]),
+    "otp_conv2d_tc_pack": (i32, [vp, i32, i32, i32, i32, vp, sz, vp]),
+    "otp_conv2d_tc": (i32, [vp, i64, vp, i64, vp, vp, vp, i64, vp, i64, i32, i32, i32, i32, i32, i32, i32, i32,
+                            vp]),
     "otp_offset_mask_pack_bytes": (sz, []),
     "otp_offset_mask_pack": (i32, [vp, vp, i32, i32, vp, sz, vp]),
     "otp_offset_mask_dcn_forward": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, i32, vp]),

@@ -25,7 +25,7 @@ from torch import nn
 
 from .. import _lib
 from .ConvVideoTransformer import ConvTransformer
-from .RSB import CHAIN_RSB_BLOCKS
+from .RSB import CHAIN_RSB_BLOCKS, conv_bn_relu
 from .layers import DeformableCONV
 from ..thirdparty.deform_conv import ModulatedDeformConv
 
@@ -219,6 +219,11 @@ class OTPose(nn.Module):
                     cat.data_ptr() + 4 * i * j * t, 3 * j * t, st), "otp_pyramid_conv1x1")
                 del s0, s1, s2
             del x1, x2
+            if getattr(self, "_rsb_precision", None) != self.precision:   # RSB convs follow the head's precision
+                for mod in self.modules():
+                    if isinstance(mod, conv_bn_relu):
+                        mod.precision = self.precision
+                self._rsb_precision = self.precision
             def_heatmaps = self.def_fuse(total_b)
             cat[:, 2 * j:].copy_(def_heatmaps)
             trans = self.offset_mask_combine_conv(cat)

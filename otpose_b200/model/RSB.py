@@ -27,6 +27,8 @@ class conv_bn_relu(nn.Module):
         self.kernel_size = kernel_size
         self._folded = None
         self._folded_key = None
+        self._tc_packed = {}
+        self.precision = "fp32"     # "fp16" / "bf16": tcgen05 implicit-GEMM path (set by OTPose)
 
     def folded(self):
         """(weight, bias) with the eval-mode BatchNorm affine folded in (RSB.py:120-131)."""
@@ -50,6 +52,20 @@ class conv_bn_relu(nn.Module):
         wt, bias = self.folded()
         relu = self.has_relu if relu is None else relu
         lib = _lib.load()
+        cin, cout, k = self.conv.in_channels, self.conv.out_channels, self.kernel_size
+        if self.precision != "fp32" and lib.otp_conv2d_tc_supported(cin, cout, h, w, k):
+            prec = _lib.precision_code(self.precision)
+            key = (self._folded_key, prec)
+            if self._tc_packed.get("key") != key:
+                nbytes = lib.otp_conv2d_tc_pack_bytes(cin, cout, k)
+                buf = torch.empty(nbytes, dtype=torch.uint8, device=wt.device)
+                _lib.check(lib.otp_conv2d_tc_pack(wt.data_ptr(), cin, cout, k, prec, buf.data_ptr(), nbytes,
+                                                  _lib.stream_ptr(wt.device)), "otp_conv2d_tc_pack")
+                self._tc_packed = {"key": key, "buf": buf}
+            _lib.check(lib.otp_conv2d_tc(x, x_bs, x_add, x_add_bs, self._tc_packed["buf"].data_ptr(), bias.data_ptr(),
+                                         residual, residual_bs, out, out_bs, b, cin, h, w, cout, k, int(relu), prec,
+                                         _lib.stream_ptr(wt.device)), "otp_conv2d_tc")
+            return
         _lib.check(lib.otp_conv2d(x, x_bs, x_add, x_add_bs, wt.data_ptr(), bias.data_ptr(), residual,
                                   residual_bs, out, out_bs, b, self.conv.in_channels, h, w,
                                   self.conv.out_channels, self.kernel_size, 1, int(relu),

@@ -81,3 +81,46 @@ def test_mn_major_view_of_the_same_tile_gram():
     got1 = run(qi, ki, 80, 128 // 16, dict(off=cs, lbo=rs, sbo=cs, kstep=2 * rs, mn=1),
                dict(off=8 * cs, lbo=rs, sbo=cs, kstep=2 * rs, mn=1))
     assert relerr(got1, ref1) < 1e-5
+
+
+@pytest.mark.parametrize("prec,tol", [("fp16", 1e-3), ("bf16", 8e-3)])
+@pytest.mark.parametrize("cin,cout,k,b,h,w,add,res", [
+    (20, 20, 3, 2, 96, 72, True, False),     # RSB 3x3 of offset_mask_combine_conv, fused input add
+    (13, 13, 3, 2, 24, 16, False, False),
+    (6, 6, 3, 3, 16, 8, True, False),        # def_fuse branch convs; map smaller than one tile
+    (51, 80, 1, 2, 96, 72, False, False),    # conv_bn_relu1 (1x1, wide)
+    (80, 32, 1, 2, 24, 16, False, True),     # conv_bn_relu3 with the block residual, 10 staged items / thread
+    (17, 24, 1, 1, 8, 8, False, False),
+    (20, 20, 3, 1, 128, 96, False, False),   # BASELINE config 5 map size
+])
+def test_tensor_core_conv_vs_float64(cin, cout, k, b, h, w, add, res, prec, tol):
+    """a7, 16-bit path: implicit-GEMM conv on tcgen05 (three pre-shifted 16-bit copies of the input
+    rows, no im2col tile) + folded BatchNorm + ReLU + fused add / residual vs a float64 CPU conv."""
+    import torch.nn.functional as F
+    from otpose_b200.model.RSB import conv_bn_relu
+    torch.manual_seed(cin * 100 + cout)
+    m = conv_bn_relu(cin, cout, k, 1, k // 2).eval()
+    with torch.no_grad():
+        m.bn.running_mean.normal_()
+        m.bn.running_var.uniform_(0.5, 2)
+        m.bn.weight.uniform_(0.5, 1.5)
+        m.bn.bias.normal_()
+    x = torch.randn(b, cin, h, w)
+    xa = torch.randn_like(x) if add else None
+    r = torch.randn(b, cout, h, w) if res else None
+    wt, bias = m.folded()
+    ref = F.conv2d((x + (xa if add else 0)).double(), wt.double(), bias.double(), padding=k // 2)
+    ref = F.relu(ref + (r.double() if res else 0))
+    m = m.cuda()
+    assert _lib.load().otp_conv2d_tc_supported(cin, cout, h, w, k) == 1
+    xg, xag, rg = x.cuda(), xa.cuda() if add else None, r.cuda() if res else None
+    for p, t in (("fp32", 1e-5), (prec, tol)):
+        m.precision = p
+        y = torch.empty(b, cout, h, w, device="cuda")
+        m.run(xg.data_ptr(), cin * h * w, y.data_ptr(), cout * h * w, b, h, w,
+              x_add=xag.data_ptr() if add else None, x_add_bs=cin * h * w,
+              residual=rg.data_ptr() if res else None, residual_bs=cout * h * w)
+        err = float((y.cpu().double() - ref).abs().max() / ref.abs().max())
+        assert err < t, (p, err)
+    # shapes the tensor-core path does not take fall back to the CUDA-core kernel (w % 8 != 0)
+    assert _lib.load().otp_conv2d_tc_supported(cin, cout, 9, 7, k) == 0
