@@ -257,13 +257,38 @@ def run_b200(args):
         out = model.forward_head(rough, margin)[0]
         return heatmap.final_preds_cuda(out, center, scale)
 
+    # end to end through the public API: every step copies ITS inputs from pinned host memory and
+    # reads its result back.  Double-buffered: the copy of step i+1 runs on a copy stream while step i
+    # computes (forward_head is asynchronous on the caller's stream), as a serving loop would do.
+    copy_stream = torch.cuda.Stream(device=dev)
+    stages = [(rough_stage, margin_stage), (torch.empty_like(rough), torch.empty_like(margin))]
+    ev_ready = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_free = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_state = {"i": 0}
+
+    def issue_copy(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_free[slot])      # the step that last used this slot has consumed it
+            stages[slot][0].copy_(rough_host, non_blocking=True)
+            stages[slot][1].copy_(margin_host, non_blocking=True)
+            ev_ready[slot].record(copy_stream)
+
     def step_e2e():
-        rough_stage.copy_(rough_host, non_blocking=True)
-        margin_stage.copy_(margin_host, non_blocking=True)
-        out = model.forward_head(rough_stage, margin_stage)[0]
+        main = torch.cuda.current_stream(dev)
+        i = e2e_state["i"]
+        slot = i & 1
+        if i == 0:
+            ev_free[0].record(main)
+            ev_free[1].record(main)
+            issue_copy(0)
+        issue_copy(slot ^ 1)                           # next step's inputs, overlapped with this step
+        main.wait_event(ev_ready[slot])
+        out = model.forward_head(stages[slot][0], stages[slot][1])[0]
+        ev_free[slot].record(main)
         r = heatmap.final_preds_cuda(out, center, scale)
         preds_host.copy_(r["preds"], non_blocking=True)
         vals_host.copy_(r["maxvals"], non_blocking=True)
+        e2e_state["i"] = i + 1
 
     def barrier():
         if world > 1:
@@ -287,11 +312,14 @@ def run_b200(args):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     wall0 = time.time()
     launches0 = lib.otp_launch_count()
+    ms = timed(step_resident, args.steps)          # the headline: no per-kernel events in the timed region
+    launches = lib.otp_launch_count() - launches0
+    # per-kernel table / roofline: a second pass of the same K steps with the library's CUDA events
+    # around every launch (2 events x ~190 launches per step cost ~7 % of the step, hence separate)
     lib.otp_profile_enable(1)
-    ms = timed(step_resident, args.steps)
+    ms_profiled = timed(step_resident, args.steps)
     prof = _lib.profile_read()
     lib.otp_profile_enable(0)
-    launches = lib.otp_launch_count() - launches0
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
@@ -322,7 +350,9 @@ def run_b200(args):
         roofline = {"kernel": top, "bound": tk["bound"], "achieved": tk["achieved"], "peak": peaks[tk["bound"]],
                     "unit": tk["unit"], "frac": tk["frac"], "traffic": traffic,
                     "peak_source": f"{peaks['source']} ({'sustained bf16' if tk['bound'] == 'tensor' else 'copy'})",
-                    "share_of_step": round(tk["ms_per_step"] / (ms / args.steps), 4)}
+                    "share_of_step": round(tk["ms_per_step"] / (ms_profiled / args.steps), 4),
+                    "timing": "CUDA events around every launch of this kernel in a separate pass of the same "
+                              f"{args.steps} steps ({ms_profiled / args.steps:.3f} ms/step with events)"}
         line = {"metric": METRIC, "value": b * world * args.steps / (ms * 1e-3), "unit": "clips/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -331,7 +361,10 @@ def run_b200(args):
                 "e2e": {"value": b * world * args.steps / (ms_e2e * 1e-3), "unit": "clips/s",
                         "h2d_bytes_per_step": rough_host.numel() * 4 + margin_host.numel() * 8,
                         "d2h_bytes_per_step": preds_host.numel() * 4 + vals_host.numel() * 4,
-                        "ms_per_step": ms_e2e / args.steps},
+                        "ms_per_step": ms_e2e / args.steps,
+                        "pipeline": "double-buffered: step i+1's pinned-host -> device copy runs on a copy stream "
+                                    "while step i computes; every step's copy and result read-back are inside "
+                                    "the timed region"},
                 "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels}
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference(args.cpu_clips, 3, 1)

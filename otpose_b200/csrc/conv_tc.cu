@@ -45,6 +45,16 @@ __host__ __device__ inline ConvTcShape conv_tc_shape(int cin, int cout, int k, i
 
 // kU = staged items per thread kept in flight (loads issued before the first use); kMinCta sizes the
 // register budget so that as many CTAs as the shared memory allows are resident per SM.
+// the CTA-wide sync that publishes the TMEM base address, the mbarrier init and the cp.async'ed weights
+__device__ __forceinline__ uint32_t tmem_slot_after_sync(const uint32_t *slot) {
+  cp_async_wait<0>();
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return *slot;
+}
+
 template <bool F16, int kU, int kMinCta>
 __global__ void __launch_bounds__(kCtThreads, kMinCta)
 conv_tc_kernel(const float *__restrict__ x, long long x_bs, const float *__restrict__ x_add, long long xa_bs,
@@ -62,7 +72,7 @@ conv_tc_kernel(const float *__restrict__ x, long long x_bs, const float *__restr
   const int P = H * W;
   const int cg = S.cpad / 8, wch = W / 8;
   const int halo = k == 3 ? wch : 0;   // chunks staged before the tile's first pixel
-  const uint32_t ncols = S.npad <= 32 ? 32 : (S.npad <= 64 ? 64 : 128);
+  const uint32_t ncols = S.npad <= 16 ? 32 : (S.npad <= 32 ? 64 : (S.npad <= 64 ? 128 : 256));   // two accumulators
 
   // weights: contiguous 16-bit operand image (K-major rows of taps*cpad)
   for (uint32_t o = threadIdx.x * 16; o < S.w_bytes; o += kCtThreads * 16) cp_async16(wsm + o, wimg + o);
@@ -146,67 +156,81 @@ conv_tc_kernel(const float *__restrict__ x, long long x_bs, const float *__restr
     }
   };
 
-  // persistent over (image, tile): TMEM, barrier and weights are set up once per CTA; the next
-  // tile's global loads are in flight while the tensor core and the epilogue work on this one
-  uint32_t phase = 0;
-  const int total = tiles * B;
-  if ((int)blockIdx.x < total) load_tile(blockIdx.x);
-  cp_async_wait<0>();
-  for (int g = blockIdx.x; g < total; g += gridDim.x) {
-    const int b = g / tiles, p0 = (g % tiles) * kCtTM;
+  // Persistent over (image, tile): TMEM, barrier and weights are set up once per CTA.  Software
+  // pipeline, two accumulators in TMEM: the UMMAs of tile n+1 are issued BEFORE the epilogue of
+  // tile n, and the global loads of tile n+2 are in flight across that epilogue.  The proxy fence
+  // sits right after the accumulator wait, where no global store of this thread is outstanding
+  // any more (fence.proxy.async waits for the thread's pending memory operations).
+  const uint32_t tm = tmem_slot_after_sync(&tmem_slot);
+  const int total = tiles * B, stepg = gridDim.x;
+  auto issue = [&](uint32_t acc) {   // warp 0, converged: the UMMA chain of the staged tile
+    const uint32_t idesc = make_idesc_16(S.npad, true, false, F16 ? 0u : 1u);
+    const uint32_t sa = smem_u32(stg), sw = smem_u32(wsm);
+    const uint32_t rsw = (uint32_t)(S.kdim / 8) * 128;   // weight image row-group stride
+    const int ks = S.cpad / 16;
+    uint32_t first = 1;
+    for (int t = 0; t < S.taps; ++t) {
+      const int dy = k == 3 ? t / 3 - 1 : 0, dxi = k == 3 ? t % 3 : 0;
+      const uint32_t a0 = sa + dxi * S.s_bytes + (uint32_t)((halo + dy * wch) * cg) * 128;
+      const uint32_t b0 = sw + (uint32_t)(t * S.cpad / 8) * 128;
+      for (int s = 0; s < ks; ++s) {
+        const uint64_t ad = make_desc(a0 + s * 256, 128, (uint32_t)cg * 128);   // LBO: next 8 channels, SBO: next 8 pixels
+        const uint64_t bd = make_desc(b0 + s * 256, 128, rsw);
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\t"
+            "elect.sync _|q, 0xffffffff;\n\t"
+            "setp.eq.b32 p, %4, 0;\n\t"
+            "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(acc), "l"(ad), "l"(bd), "r"(idesc), "r"(first)
+            : "memory");
+        first = 0;
+      }
+    }
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(smem_u32(&bar))
+        : "memory");
+  };
+  auto stage_and_issue = [&](uint32_t acc) {   // registers -> staged copies -> UMMAs into accumulator acc
     store_tile();
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tm = tmem_slot;
-    if (warp == 0) {
-      const uint32_t idesc = make_idesc_16(S.npad, true, false, F16 ? 0u : 1u);
-      const uint32_t sa = smem_u32(stg), sw = smem_u32(wsm);
-      const uint32_t rsw = (uint32_t)(S.kdim / 8) * 128;   // weight image row-group stride
-      const int ks = S.cpad / 16;
-      uint32_t first = 1;
-      for (int t = 0; t < S.taps; ++t) {
-        const int dy = k == 3 ? t / 3 - 1 : 0, dxi = k == 3 ? t % 3 : 0;
-        const uint32_t a0 = sa + dxi * S.s_bytes + (uint32_t)((halo + dy * wch) * cg) * 128;
-        const uint32_t b0 = sw + (uint32_t)(t * S.cpad / 8) * 128;
-        for (int s = 0; s < ks; ++s) {
-          const uint64_t ad = make_desc(a0 + s * 256, 128, (uint32_t)cg * 128);   // LBO: next 8 channels, SBO: next 8 pixels
-          const uint64_t bd = make_desc(b0 + s * 256, 128, rsw);
-          asm volatile(
-              "{\n\t.reg .pred p, q;\n\t"
-              "elect.sync _|q, 0xffffffff;\n\t"
-              "setp.eq.b32 p, %4, 0;\n\t"
-              "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-              ::"r"(tm), "l"(ad), "l"(bd), "r"(idesc), "r"(first)
-              : "memory");
-          first = 0;
-        }
-      }
-      asm volatile(
-          "{\n\t.reg .pred q;\n\t"
-          "elect.sync _|q, 0xffffffff;\n\t"
-          "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
-          ::"r"(smem_u32(&bar))
-          : "memory");
-    }
-    if (g + (int)gridDim.x < total) load_tile(g + gridDim.x);
-    mbar_wait(&bar, phase);
+    if (warp == 0) issue(acc);
+  };
+  uint32_t phase = 0, n = 0;
+  int g = blockIdx.x;
+  if (g < total) {
+    load_tile(g);
+    stage_and_issue(tm);
+    if (g + stepg < total) load_tile(g + stepg);
+  }
+  for (; g < total; g += stepg, ++n) {
+    const int b = g / tiles, p0 = (g % tiles) * kCtTM;
+    const uint32_t acc = tm + (n & 1) * S.npad;
+    mbar_wait(&bar, phase);   // tile n: accumulator ready, staged copies free
     phase ^= 1;
     tc_fence_after();
-    // ---- epilogue: lane == pixel, column == output channel ----
+    if (g + stepg < total) {
+      stage_and_issue(tm + ((n + 1) & 1) * S.npad);   // tile n+1 (v[] holds its data)
+      if (g + 2 * stepg < total) load_tile(g + 2 * stepg);
+    }
+    // ---- epilogue of tile n: lane == pixel, column == output channel ----
     {
       const int p = p0 + warp * 32 + lane;
       const bool live = p < P;
       float *yp = y + (size_t)b * y_bs + p;
       const float *rp = residual ? residual + (size_t)b * r_bs + p : nullptr;
       for (int n0 = 0; n0 < S.npad; n0 += 16) {
-        float acc[16];
-        tmem_ld16(tm + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0, acc);
+        float a16[16];
+        tmem_ld16(acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0, a16);
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           if (n0 + e < cout && live) {
-            float o = acc[e] + sbias[n0 + e];
+            float o = a16[e] + sbias[n0 + e];
             if (rp) o += __ldg(rp);
             if (relu) o = fmaxf(o, 0.f);
             *yp = o;
@@ -216,9 +240,10 @@ conv_tc_kernel(const float *__restrict__ x, long long x_bs, const float *__restr
         }
       }
     }
-    tc_fence_before();
-    __syncthreads();   // staging buffers / accumulator are reused by the next tile
+    tc_fence_before();   // this accumulator is rewritten by the UMMAs issued after the next __syncthreads
   }
+  tc_fence_before();
+  __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_slot, ncols);
 }
 
@@ -311,7 +336,9 @@ extern "C" int otp_conv2d_tc(const float *x, long long x_bstride, const float *x
   conv_tc_kernel<F16, U, MINCTA><<<min(total, num_sms() * min(MINCTA, max_cta)), kCtThreads, S.smem, st>>>(           \
       x, x_bstride, x_add, x_add_bstride, pk, bias, residual, residual_bstride, y, y_bstride, b, cin, h, w, cout, k, \
       relu, tiles)
-  const int max_cta = max(1, (int)((227 * 1024) / (S.smem + 2048)));   // resident CTAs the shared memory allows
+  // resident CTAs that shared memory and the 512 TMEM columns (two accumulators per CTA) allow
+  const int tcols = S.npad <= 16 ? 32 : (S.npad <= 32 ? 64 : (S.npad <= 64 ? 128 : 256));
+  const int max_cta = max(1, min((int)((227 * 1024) / (S.smem + 2048)), 512 / tcols));
   const int per_thread = ceil_div(S.cpad * (int)S.s_chunks, kCtThreads);
   const bool f16 = precision == OTP_PREC_FP16;
   if (per_thread <= 3) {
