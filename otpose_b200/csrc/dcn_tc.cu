@@ -25,7 +25,8 @@ using namespace tc;
 namespace {
 constexpr int kJ = 17, kCin = 32, kTaps = 9;
 constexpr int kTM = 128, kThreads = 384;   // thread = (pixel, third): 3 taps / 3 joints each
-constexpr int kNPad = 256;                        // UMMA N (>= 27 * 9 = 243)
+constexpr int kNPad = 256;                        // UMMA N (>= 28 * 9 = 252)
+constexpr int kJRows = 28;                        // accumulator columns per joint
 constexpr uint32_t kCS = 128, kRS32 = (kCin / 8) * 128;   // 512
 constexpr uint32_t kATap = (kTM / 8) * kRS32;     // 8192   [128 px][32 ch]
 constexpr uint32_t kWTap = (kNPad / 8) * kRS32;   // 16384  [256 rows][32 ch]
@@ -33,7 +34,8 @@ constexpr uint32_t kWSlice = kTaps * kWTap;       // 147456 one joint-half
 constexpr uint32_t kASlice = kTaps * kATap;       // 73728
 constexpr int kJ0[2] = {0, 9}, kNJ[2] = {9, 8};
 constexpr size_t kPackBytes = (size_t)2 * 2 * kWSlice;   // [format][joint half]
-constexpr size_t kSmem = (size_t)kWSlice + kASlice + (size_t)kJ * 81 * 4 + 64;
+constexpr int kWdLd = 20;                         // DCN weight row: 17 outputs padded to 5 float4
+constexpr size_t kSmem = (size_t)kWSlice + kASlice + (size_t)81 * kWdLd * 4 + 64;
 static_assert(kSmem + 1024 <= 227 * 1024, "fused DCN shared memory");
 
 __device__ __forceinline__ void tmem_ldn(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
@@ -60,7 +62,7 @@ tc_dcn_fused_kernel(const uint8_t *__restrict__ wimg, const float *__restrict__ 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *ws = smem;                         // 9 x [256][32] conv weights, resident
   uint8_t *as = smem + kWSlice;               // 9 x [128][32] im2col taps; later the partial-sum exchange
-  float *wd = reinterpret_cast<float *>(as + kASlice);   // [17][nj*9] DCN weight slice
+  float *wd = reinterpret_cast<float *>(as + kASlice);   // [nj*9][20] DCN weight slice, output channel fastest
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -69,9 +71,9 @@ tc_dcn_fused_kernel(const uint8_t *__restrict__ wimg, const float *__restrict__ 
 
   for (uint32_t o = threadIdx.x * 16; o < kWSlice; o += kThreads * 16) cp_async16(ws + o, wimg + o);
   cp_async_commit();
-  for (int e = threadIdx.x; e < kJ * nj * 9; e += kThreads) {
-    const int o = e / (nj * 9), r = e % (nj * 9);
-    wd[o * 81 + r] = dcn_w[(size_t)o * kJ * 9 + j0 * 9 + r];
+  for (int e = threadIdx.x; e < nj * 9 * kWdLd; e += kThreads) {
+    const int r = e / kWdLd, o = e % kWdLd;
+    wd[e] = o < kJ ? dcn_w[(size_t)o * kJ * 9 + j0 * 9 + r] : 0.f;
   }
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
@@ -87,7 +89,6 @@ tc_dcn_fused_kernel(const uint8_t *__restrict__ wimg, const float *__restrict__ 
   uint32_t ph = 0;
   // joints of this thread in the DCN phase: the CTA's nj joints split over the three thread thirds
   const int jl_lo = 3 * third, jl_hi = min(nj, 3 * third + 3);
-  const int msk_col0 = 18 * nj;
 
   for (int g = blockIdx.x; g < B * tiles; g += gridDim.x) {
     const int b = g / tiles, tile = g % tiles;
@@ -97,18 +98,24 @@ tc_dcn_fused_kernel(const uint8_t *__restrict__ wimg, const float *__restrict__ 
     // ---- im2col: this thread's 3 of the 9 dilated taps, all 32 channels (96 loads in flight) ----
     {
       const float *tb = trans + (size_t)b * kCin * P;
+      float v[3][kCin];
 #pragma unroll
       for (int tt = 0; tt < 3; ++tt) {
         const int t = 3 * third + tt;
         const int hh = h + (t / 3 - 1) * dil, ww = w + (t % 3 - 1) * dil;
         const bool ok = live && hh >= 0 && hh < H && ww >= 0 && ww < W;
         const float *src = tb + (ok ? hh * W + ww : 0);
-        float v[kCin];
 #pragma unroll
-        for (int c = 0; c < kCin; ++c) v[c] = ok ? __ldg(src + (size_t)c * P) : 0.f;
-        uint8_t *dst = as + t * kATap + cm_offset(tok, 0, kRS32, kCS);
+        for (int c = 0; c < kCin; ++c) {
+          v[tt][c] = ok ? __ldg(src) : 0.f;
+          src += P;
+        }
+      }
 #pragma unroll
-        for (int g = 0; g < kCin / 8; ++g) *reinterpret_cast<uint4 *>(dst + g * kCS) = pack16x8<F16>(v + 8 * g);
+      for (int tt = 0; tt < 3; ++tt) {
+        uint8_t *dst = as + (3 * third + tt) * kATap + cm_offset(tok, 0, kRS32, kCS);
+#pragma unroll
+        for (int g = 0; g < kCin / 8; ++g) *reinterpret_cast<uint4 *>(dst + g * kCS) = pack16x8<F16>(v[tt] + 8 * g);
       }
     }
     fence_async_smem();
@@ -138,29 +145,53 @@ tc_dcn_fused_kernel(const uint8_t *__restrict__ wimg, const float *__restrict__ 
     for (int jl = jl_lo; jl < jl_hi; ++jl) {
       float off[18], msk[9];
       {
-        float t16[16];
-        tmem_ldn(trow + 18 * jl, t16);
+        // 28 consecutive columns of this joint: x16 + x8 + x4 loads, one wait
+        uint32_t r0[16], r1[8], r2[4];
+        const uint32_t ta = trow + kJRows * jl;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(r0[0]), "=r"(r0[1]), "=r"(r0[2]), "=r"(r0[3]), "=r"(r0[4]), "=r"(r0[5]), "=r"(r0[6]), "=r"(r0[7]),
+              "=r"(r0[8]), "=r"(r0[9]), "=r"(r0[10]), "=r"(r0[11]), "=r"(r0[12]), "=r"(r0[13]), "=r"(r0[14]), "=r"(r0[15])
+            : "r"(ta)
+            : "memory");
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]), "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7])
+                     : "r"(ta + 16)
+                     : "memory");
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3])
+                     : "r"(ta + 24)
+                     : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int i = 0; i < 16; ++i) off[i] = t16[i];
-        tmem_ld2(trow + 18 * jl + 16, off[16], off[17]);
-        float m8[8];
-        tmem_ld8(trow + msk_col0 + 9 * jl, m8);
+        for (int i = 0; i < 16; ++i) asm volatile("" : "+r"(r0[i])::"memory");
 #pragma unroll
-        for (int i = 0; i < 8; ++i) msk[i] = m8[i];
-        tmem_ld1(trow + msk_col0 + 9 * jl + 8, msk[8]);
+        for (int i = 0; i < 8; ++i) asm volatile("" : "+r"(r1[i])::"memory");
+#pragma unroll
+        for (int i = 0; i < 4; ++i) asm volatile("" : "+r"(r2[i])::"memory");
+#pragma unroll
+        for (int i = 0; i < 16; ++i) off[i] = __uint_as_float(r0[i]);
+        off[16] = __uint_as_float(r1[0]);
+        off[17] = __uint_as_float(r1[1]);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) msk[i] = __uint_as_float(r1[2 + i]);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) msk[6 + i] = __uint_as_float(r2[i]);
       }
       if (live) {
         const float *img = xb + (size_t)(j0 + jl) * P;
         // Branch-free bilinear taps (same arithmetic as dmcn_im2col_bilinear): out-of-range corners
         // get weight 0 and a clamped address, so the 12 loads of a tap triple are independent
-        // and in flight together instead of sitting behind data-dependent branches.
+        // and in flight together instead of sitting behind data-dependent branches.  Two rounds
+        // (taps 0-4, 5-8): 20 + 16 gathers in flight.
 #pragma unroll
-        for (int tg = 0; tg < 3; ++tg) {
-          float wgt[3][4];
-          int adr[3][4];
+        for (int tg = 0; tg < 2; ++tg) {
+          float wgt[5][4];
+          int adr[5][4];
 #pragma unroll
-          for (int u = 0; u < 3; ++u) {
-            const int t = 3 * tg + u;
+          for (int u = 0; u < 5; ++u) {
+            const int t = 5 * tg + u;
+            if (t >= kTaps) continue;
             const float h_im = (float)(h + (t / 3 - 1) * dil) + off[2 * t];
             const float w_im = (float)(w + (t % 3 - 1) * dil) + off[2 * t + 1];
             const bool in = h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W;
@@ -181,38 +212,50 @@ tc_dcn_fused_kernel(const uint8_t *__restrict__ wimg, const float *__restrict__ 
             adr[u][2] = hc1 * W + wc0;
             adr[u][3] = hc1 * W + wc1;
           }
-          float val[3][4];
+          float val[5][4];
 #pragma unroll
-          for (int u = 0; u < 3; ++u)
+          for (int u = 0; u < 5; ++u)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) val[u][q] = __ldg(img + adr[u][q]);
+            for (int q = 0; q < 4; ++q)
+              if (5 * tg + u < kTaps) val[u][q] = __ldg(img + adr[u][q]);
 #pragma unroll
-          for (int u = 0; u < 3; ++u) {
-            const int t = 3 * tg + u;
+          for (int u = 0; u < 5; ++u) {
+            const int t = 5 * tg + u;
+            if (t >= kTaps) continue;
             const float v = wgt[u][0] * val[u][0] + wgt[u][1] * val[u][1] + wgt[u][2] * val[u][2] +
                             wgt[u][3] * val[u][3];
             const float col = v * msk[t];
-            const float *wr = wd + jl * 9 + t;
+            const float4 *wr = reinterpret_cast<const float4 *>(wd + (jl * 9 + t) * kWdLd);
 #pragma unroll
-            for (int o = 0; o < kJ; ++o) acc[o] = fmaf(wr[o * 81], col, acc[o]);
+            for (int q = 0; q < 4; ++q) {
+              const float4 w4 = wr[q];
+              acc[4 * q] = fmaf(w4.x, col, acc[4 * q]);
+              acc[4 * q + 1] = fmaf(w4.y, col, acc[4 * q + 1]);
+              acc[4 * q + 2] = fmaf(w4.z, col, acc[4 * q + 2]);
+              acc[4 * q + 3] = fmaf(w4.w, col, acc[4 * q + 3]);
+            }
+            acc[16] = fmaf(wr[4].x, col, acc[16]);
           }
         }
       }
     }
-    // ---- combine the three thread thirds (exchange buffer aliases the dead im2col taps) ----
+    // ---- combine the three thread thirds (exchange buffer aliases the dead im2col taps): every
+    //      thread publishes its 17 partial sums, then third q reduces and stores outputs q, q+3, ... ----
     float *ex = reinterpret_cast<float *>(as);
-    if (third > 0) {
 #pragma unroll
-      for (int o = 0; o < kJ; ++o) ex[((third - 1) * kJ + o) * kTM + tok] = acc[o];
-    }
+    for (int o = 0; o < kJ; ++o) ex[(third * kJ + o) * kTM + tok] = acc[o];
     tc_fence_before();
     __syncthreads();
-    if (third == 0 && live) {
+    if (live) {
 #pragma unroll
-      for (int o = 0; o < kJ; ++o) {
-        float v = acc[o] + ex[o * kTM + tok] + ex[(kJ + o) * kTM + tok] + (dcn_b ? __ldg(dcn_b + o) : 0.f);
-        float *dst = out + ((size_t)b * kJ + o) * P + p;
-        *dst = accumulate ? fmaf(alpha, v, *dst) : alpha * v;
+      for (int i = 0; i < (kJ + 2) / 3; ++i) {
+        const int o = third + 3 * i;
+        if (o < kJ) {
+          const float v = ex[o * kTM + tok] + ex[(kJ + o) * kTM + tok] + ex[(2 * kJ + o) * kTM + tok] +
+                          (dcn_b ? __ldg(dcn_b + o) : 0.f);
+          float *dst = out + ((size_t)b * kJ + o) * P + p;
+          *dst = accumulate ? fmaf(alpha, v, *dst) : alpha * v;
+        }
       }
     }
     __syncthreads();   // exchange buffer / TMEM are rewritten by the next tile
@@ -223,7 +266,8 @@ tc_dcn_fused_kernel(const uint8_t *__restrict__ wimg, const float *__restrict__ 
   if (warp == 0) tmem_dealloc(tm, 256);
 }
 
-// image row r of joint-half hf: offsets of its joints (18 each), then their masks (9 each)
+// image row r of joint-half hf: 28 rows per joint (18 offsets, 9 masks, one zero row), so that a
+// thread reads a joint's 27 values with one batch of tcgen05.ld and a single wait
 template <bool F16>
 __global__ void pack_offset_mask_kernel(const float *__restrict__ w_off, const float *__restrict__ w_msk,
                                         uint8_t *__restrict__ dst, int j0, int nj) {
@@ -231,8 +275,9 @@ __global__ void pack_offset_mask_kernel(const float *__restrict__ w_off, const f
   if (e >= kTaps * kNPad * kCin) return;
   const int c = e % kCin, r = (e / kCin) % kNPad, t = e / (kCin * kNPad);
   float v = 0.f;
-  if (r < 18 * nj) v = w_off[((size_t)(j0 * 18 + r) * kCin + c) * 9 + t];
-  else if (r < 27 * nj) v = w_msk[((size_t)(j0 * 9 + r - 18 * nj) * kCin + c) * 9 + t];
+  const int jl = r / kJRows, i = r % kJRows;   // per joint: 18 offset rows, 9 mask rows, 1 zero row
+  if (jl < nj && i < 18) v = w_off[((size_t)((j0 + jl) * 18 + i) * kCin + c) * 9 + t];
+  else if (jl < nj && i < 27) v = w_msk[((size_t)((j0 + jl) * 9 + i - 18) * kCin + c) * 9 + t];
   *reinterpret_cast<unsigned short *>(dst + (size_t)t * kWTap + cm_offset(r, c, kRS32, kCS)) = to16<F16>(v);
 }
 
