@@ -133,45 +133,81 @@ upsample_kernel(const float *__restrict__ x, float *__restrict__ y, int Tin, int
 }
 
 // model/OTPose.py:362-373: out[o,t] = bias[o] + sum_{s,c} W[o, s*C+c] * up_s(src_s)[c,t]
+// Weight rows are padded to a multiple of 4 outputs and read as float4 broadcasts, and every thread
+// produces TWO tokens (t and t + 256) per weight read: the kernel is bound by the shared-memory
+// weight traffic per FMA, not by HBM.
 template <int CO>
 __global__ void __launch_bounds__(kFuThreads)
 pyramid_conv_kernel(const float *__restrict__ s0, const float *__restrict__ s1,
                     const float *__restrict__ s2, int C, int T, int T1, int T2,
                     const float *__restrict__ weight, const float *__restrict__ bias, int Cout,
                     float *__restrict__ out, long long out_bstride) {
-  extern __shared__ float ws[];  // [3C][CO]
+  constexpr int LD = (CO + 3) / 4 * 4;
+  extern __shared__ __align__(16) float ws[];  // [3C][LD]
   const int co0 = blockIdx.z * CO;
-  for (int e = threadIdx.x; e < 3 * C * CO; e += kFuThreads) {
-    int o = e % CO, k = e / CO;
-    ws[e] = (co0 + o < Cout) ? __ldg(weight + (size_t)(co0 + o) * 3 * C + k) : 0.f;
+  for (int e = threadIdx.x; e < 3 * C * LD; e += kFuThreads) {
+    int o = e % LD, k = e / LD;
+    ws[e] = (o < CO && co0 + o < Cout) ? __ldg(weight + (size_t)(co0 + o) * 3 * C + k) : 0.f;
   }
   __syncthreads();
-  const int t = blockIdx.x * kFuThreads + threadIdx.x;
   const int b = blockIdx.y;
-  if (t >= T) return;
-  float acc[CO];
+  int tk[2];
+  tk[0] = blockIdx.x * 2 * kFuThreads + threadIdx.x;
+  tk[1] = tk[0] + kFuThreads;
+  if (tk[0] >= T) return;
+  const bool two = tk[1] < T;
+  float acc[2][LD];
 #pragma unroll
-  for (int o = 0; o < CO; ++o) acc[o] = 0.f;
-  int a0, a1, b0, b1;
-  float la, lb;
-  lerp_index(t, 0.5f, T1, a0, a1, la);
-  lerp_index(t, 0.25f, T2, b0, b1, lb);
-  const float *p0 = s0 + (size_t)b * C * T + t;
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int o = 0; o < LD; ++o) acc[u][o] = 0.f;
+  int a0[2], a1[2], b0[2], b1[2];
+  float la[2], lb[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int t = two || u == 0 ? tk[u] : tk[0];
+    lerp_index(t, 0.5f, T1, a0[u], a1[u], la[u]);
+    lerp_index(t, 0.25f, T2, b0[u], b1[u], lb[u]);
+    tk[u] = t;
+  }
+  const float *p0 = s0 + (size_t)b * C * T;
   const float *p1 = s1 + (size_t)b * C * T1;
   const float *p2 = s2 + (size_t)b * C * T2;
-#pragma unroll 8
+#pragma unroll 4
   for (int c = 0; c < C; ++c) {
-    float v0 = __ldg(p0 + (size_t)c * T);
-    float v1 = (1.f - la) * __ldg(p1 + (size_t)c * T1 + a0) + la * __ldg(p1 + (size_t)c * T1 + a1);
-    float v2 = (1.f - lb) * __ldg(p2 + (size_t)c * T2 + b0) + lb * __ldg(p2 + (size_t)c * T2 + b1);
-    const float *w0 = ws + c * CO, *w1 = ws + (C + c) * CO, *w2 = ws + (2 * C + c) * CO;
+    float v0[2], v1[2], v2[2];
 #pragma unroll
-    for (int o = 0; o < CO; ++o) acc[o] = fmaf(w0[o], v0, fmaf(w1[o], v1, fmaf(w2[o], v2, acc[o])));
+    for (int u = 0; u < 2; ++u) {
+      v0[u] = __ldg(p0 + tk[u]);
+      v1[u] = (1.f - la[u]) * __ldg(p1 + a0[u]) + la[u] * __ldg(p1 + a1[u]);
+      v2[u] = (1.f - lb[u]) * __ldg(p2 + b0[u]) + lb[u] * __ldg(p2 + b1[u]);
+    }
+    p0 += T;
+    p1 += T1;
+    p2 += T2;
+    const float4 *w0 = reinterpret_cast<const float4 *>(ws + c * LD);
+    const float4 *w1 = reinterpret_cast<const float4 *>(ws + (C + c) * LD);
+    const float4 *w2 = reinterpret_cast<const float4 *>(ws + (2 * C + c) * LD);
+#pragma unroll
+    for (int q = 0; q < LD / 4; ++q) {
+      const float4 x0 = w0[q], x1 = w1[q], x2 = w2[q];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        acc[u][4 * q] = fmaf(x0.x, v0[u], fmaf(x1.x, v1[u], fmaf(x2.x, v2[u], acc[u][4 * q])));
+        acc[u][4 * q + 1] = fmaf(x0.y, v0[u], fmaf(x1.y, v1[u], fmaf(x2.y, v2[u], acc[u][4 * q + 1])));
+        acc[u][4 * q + 2] = fmaf(x0.z, v0[u], fmaf(x1.z, v1[u], fmaf(x2.z, v2[u], acc[u][4 * q + 2])));
+        acc[u][4 * q + 3] = fmaf(x0.w, v0[u], fmaf(x1.w, v1[u], fmaf(x2.w, v2[u], acc[u][4 * q + 3])));
+      }
+    }
   }
 #pragma unroll
-  for (int o = 0; o < CO; ++o)
-    if (co0 + o < Cout)
-      out[(size_t)b * out_bstride + (size_t)(co0 + o) * T + t] = acc[o] + (bias ? __ldg(bias + co0 + o) : 0.f);
+  for (int u = 0; u < 2; ++u) {
+    if (u == 1 && !two) break;
+#pragma unroll
+    for (int o = 0; o < CO; ++o)
+      if (co0 + o < Cout)
+        out[(size_t)b * out_bstride + (size_t)(co0 + o) * T + tk[u]] = acc[u][o] + (bias ? __ldg(bias + co0 + o) : 0.f);
+  }
 }
 
 }  // namespace otp
@@ -266,16 +302,16 @@ extern "C" int otp_pyramid_conv1x1(const float *s0, const float *s1, const float
   cudaStream_t st = (cudaStream_t)stream;
   LaunchScope ls(K_PYRAMID, st);
   if (cout % 17 == 0) {
-    size_t smem = (size_t)3 * c * 17 * sizeof(float);
+    size_t smem = (size_t)3 * c * 20 * sizeof(float);
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(pyramid_conv_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    pyramid_conv_kernel<17><<<dim3(ceil_div(t, kFuThreads), b, cout / 17), kFuThreads, smem, st>>>(
+    pyramid_conv_kernel<17><<<dim3(ceil_div(t, 2 * kFuThreads), b, cout / 17), kFuThreads, smem, st>>>(
         s0, s1, s2, c, t, t1, t2, weight, bias, cout, out, out_bstride);
   } else {
     size_t smem = (size_t)3 * c * 16 * sizeof(float);
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(pyramid_conv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    pyramid_conv_kernel<16><<<dim3(ceil_div(t, kFuThreads), b, ceil_div(cout, 16)), kFuThreads, smem, st>>>(
+    pyramid_conv_kernel<16><<<dim3(ceil_div(t, 2 * kFuThreads), b, ceil_div(cout, 16)), kFuThreads, smem, st>>>(
         s0, s1, s2, c, t, t1, t2, weight, bias, cout, out, out_bstride);
   }
   return check_launch("pyramid_conv_kernel");
