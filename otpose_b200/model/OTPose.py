@@ -74,6 +74,7 @@ class OTPose(nn.Module):
         self.patch_dim = self.num_joints
         self.temporal_encoding_dim = self.patch_dim * self.num_frames
         self.precision = precision
+        self._side_streams = {}
         if extra['FINAL_CONV_KERNEL'] != 1:
             raise NotImplementedError("final_layer kernels are built for FINAL_CONV_KERNEL = 1")
         if backbone is not None:
@@ -198,6 +199,23 @@ class OTPose(nn.Module):
         with torch.cuda.device(dev):
             _lib.check(lib.otp_fusion_sum_frames(_lib.dptr(rough), frames, b, j, t, total_b.data_ptr(),
                                                  squeezed.data_ptr(), st), "otp_fusion_sum_frames")
+            if getattr(self, "_rsb_precision", None) != self.precision:   # RSB convs follow the head's precision
+                for mod in self.modules():
+                    if isinstance(mod, conv_bn_relu):
+                        mod.precision = self.precision
+                self._rsb_precision = self.precision
+            # def_fuse only needs total_b: its 25 small convs run on a side stream, concurrently with
+            # the (equally launch/latency-bound) C=17 flow encoder and the fusion prologue
+            cat = torch.empty((b, 3 * j, h, w), **f32)       # [final_layer1 | final_layer2 | def_heatmaps]
+            main = torch.cuda.current_stream(dev)
+            side = self._side_streams.get(dev.index)
+            if side is None:
+                side = self._side_streams[dev.index] = torch.cuda.Stream(device=dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                def_heatmaps = self.def_fuse(total_b)
+                cat[:, 2 * j:].copy_(def_heatmaps)
+            def_heatmaps.record_stream(main)
             ctx = self.flow_encoder(total_b)[0]                                  # (B, J, T)
             x1 = torch.empty((b, c8, t), **f32)
             x2 = torch.empty((b, c8, t), **f32)
@@ -209,7 +227,6 @@ class OTPose(nn.Module):
                 _lib.dptr(pe1, allow_none=True), _lib.dptr(pe2, allow_none=True), ps1, frames, b, j, t,
                 x1.data_ptr(), x2.data_ptr(), intersection.data_ptr(), prev_b.data_ptr(), st),
                 "otp_fusion_stack_frames")
-            cat = torch.empty((b, 3 * j, h, w), **f32)       # [final_layer1 | final_layer2 | def_heatmaps]
             for i, (enc, fl, xin) in enumerate(((self.temporal_encoder1, self.final_layer1, x1),
                                                 (self.temporal_encoder2, self.final_layer2, x2))):
                 s0, s1, s2 = enc.forward_tokens(xin)
@@ -219,13 +236,7 @@ class OTPose(nn.Module):
                     cat.data_ptr() + 4 * i * j * t, 3 * j * t, st), "otp_pyramid_conv1x1")
                 del s0, s1, s2
             del x1, x2
-            if getattr(self, "_rsb_precision", None) != self.precision:   # RSB convs follow the head's precision
-                for mod in self.modules():
-                    if isinstance(mod, conv_bn_relu):
-                        mod.precision = self.precision
-                self._rsb_precision = self.precision
-            def_heatmaps = self.def_fuse(total_b)
-            cat[:, 2 * j:].copy_(def_heatmaps)
+            main.wait_stream(side)
             trans = self.offset_mask_combine_conv(cat)
             if _debug is not None:
                 _debug.update(cat=cat, trans=trans, def_heatmaps=def_heatmaps)
