@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16", "fp16"])
     ap.add_argument("--cpu-clips", type=int, default=2, help="clips per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cuda-graph", action="store_true",
+                    help="launch the ~190 kernels of a step one by one instead of replaying OTPose's captured graph")
     ap.add_argument("--frames", type=int, default=5, choices=[3, 5, 7],
                     help="frame window (config 5 sweep; 5 = the reference's supplement)")
     ap.add_argument("--heatmap", default="96x72", help="heat-map HxW (config 5: 128x96)")
@@ -241,7 +243,7 @@ def run_b200(args):
         precision = "fp16" if lib.otp_has_tensor_core_path() else "fp32"
     b = args.batch
 
-    model = OTPose(default_cfg((H, W)), precision=precision)
+    model = OTPose(default_cfg((H, W)), precision=precision, cuda_graph=not args.no_cuda_graph)
     model.load_state_dict(syn.fill_state_dict({k: v.shape for k, v in model.state_dict().items()}, seed=2024))
     model = model.to(dev).eval()
     rough_host = syn.synth_rough_heatmaps(b, J, H, W, frames=FRAMES, seed=shard_seed(1234, rank)).pin_memory()
@@ -316,8 +318,14 @@ def run_b200(args):
     launches = lib.otp_launch_count() - launches0
     # per-kernel table / roofline: a second pass of the same K steps with the library's CUDA events
     # around every launch (2 events x ~190 launches per step cost ~7 % of the step, hence separate)
+    graph_mode = model.cuda_graph
+    model.cuda_graph = False                       # per-kernel events need the individual launches
     lib.otp_profile_enable(1)
+    launches1 = lib.otp_launch_count()
     ms_profiled = timed(step_resident, args.steps)
+    if graph_mode:   # the timed region replayed these same kernels as graph nodes: count them here
+        launches = lib.otp_launch_count() - launches1
+    model.cuda_graph = graph_mode
     prof = _lib.profile_read()
     lib.otp_profile_enable(0)
     for _ in range(2):
@@ -357,7 +365,9 @@ def run_b200(args):
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[precision], "data": "synthetic",
-                "config": workload_config(b, precision), "clocks": clocks,
+                "config": dict(workload_config(b, precision),
+                               launch="OTPose(cuda_graph=True): one captured CUDA graph replay per step"
+                               if model.cuda_graph else "eager: one launch per kernel"), "clocks": clocks,
                 "e2e": {"value": b * world * args.steps / (ms_e2e * 1e-3), "unit": "clips/s",
                         "h2d_bytes_per_step": rough_host.numel() * 4 + margin_host.numel() * 8,
                         "d2h_bytes_per_step": preds_host.numel() * 4 + vals_host.numel() * 4,

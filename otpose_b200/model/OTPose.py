@@ -63,7 +63,7 @@ def _offset_conv(nc, kh, kw, dd, dg):
 
 
 class OTPose(nn.Module):
-    def __init__(self, cfg, backbone=None, precision="fp32", **kwargs):
+    def __init__(self, cfg, backbone=None, precision="fp32", cuda_graph=False, **kwargs):
         super().__init__()
         extra = cfg['MODEL']['EXTRA']
         self.num_frames = 8
@@ -74,6 +74,8 @@ class OTPose(nn.Module):
         self.patch_dim = self.num_joints
         self.temporal_encoding_dim = self.patch_dim * self.num_frames
         self.precision = precision
+        self.cuda_graph = bool(cuda_graph)   # opt-in: replay forward_head from a captured CUDA graph
+        self._graphs = {}
         self._side_streams = {}
         if extra['FINAL_CONV_KERNEL'] != 1:
             raise NotImplementedError("final_layer kernels are built for FINAL_CONV_KERNEL = 1")
@@ -160,12 +162,69 @@ class OTPose(nn.Module):
         rough_heatmaps = self.rough_pose_estimation_net(x)
         return self.forward_head(rough_heatmaps, kwargs["margin"])
 
+    # ------------------------------------------------------------------ CUDA graph replay (opt-in)
+    def invalidate_graphs(self):
+        """Drop captured graphs (call after changing parameters in place; ``load_state_dict``, ``.to()``
+        and ``.train()`` do it themselves)."""
+        self._graphs = {}
+
+    def load_state_dict(self, *a, **k):
+        self.invalidate_graphs()
+        return super().load_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self._graphs = {}
+        return super()._apply(fn, *a, **k)
+
+    def train(self, mode=True):
+        self._graphs = {}
+        return super().train(mode)
+
     @torch.no_grad()
+    def _forward_head_graphed(self, rough_heatmaps, margin):
+        """The ~190 launches of one head forward captured once per input shape in a CUDA graph and
+        replayed: the inputs are copied into the graph's static buffers (75 MB device copy at 32 clips,
+        ~25 us), the returned tensors are the graph's static outputs -- valid until the next call."""
+        rough = rough_heatmaps if rough_heatmaps.dtype == torch.float32 else rough_heatmaps.float()
+        dev = rough.device
+        key = (dev.index, tuple(rough.shape), tuple(margin.shape), self.precision)
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) >= 4:
+                self._graphs.pop(next(iter(self._graphs)))
+            s_rough = torch.empty_like(rough, memory_format=torch.contiguous_format)
+            s_margin = torch.empty(margin.shape, dtype=torch.int64, device=dev)
+            s_rough.copy_(rough)
+            s_margin.copy_(margin)
+            warm = torch.cuda.Stream(device=dev)          # warm-up off the capture: weight packing,
+            warm.wait_stream(torch.cuda.current_stream(dev))   # workspace growth, function attributes
+            with torch.cuda.stream(warm):
+                self._forward_head_eager(s_rough, s_margin)
+                self._forward_head_eager(s_rough, s_margin)
+            torch.cuda.current_stream(dev).wait_stream(warm)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                outs = self._forward_head_eager(s_rough, s_margin)
+            ent = self._graphs[key] = (graph, s_rough, s_margin, outs)
+        graph, s_rough, s_margin, outs = ent
+        s_rough.copy_(rough, non_blocking=True)
+        s_margin.copy_(margin, non_blocking=True)
+        graph.replay()
+        return (outs[0], rough_heatmaps) + tuple(outs[2:])
+
     def forward_head(self, rough_heatmaps, margin, _debug=None):
         """model/OTPose.py:320-394.  rough_heatmaps (5B, J, H, W) fp32 CUDA ordered
         cur, prev, next, pprev, nnext; margin (B, 4) integer.  Returns the reference
         7-tuple.  ``squeezed`` is returned as a stride-0 expand of the (B,1,H,W) plane
-        (same values as the reference's J-fold stack)."""
+        (same values as the reference's J-fold stack).  With ``cuda_graph=True`` the launches are
+        replayed from a captured CUDA graph (see ``_forward_head_graphed``)."""
+        if (self.cuda_graph and _debug is None and not self.training and rough_heatmaps.is_cuda
+                and rough_heatmaps.shape[0] > 0 and not torch.cuda.is_current_stream_capturing()):
+            return self._forward_head_graphed(rough_heatmaps, margin)
+        return self._forward_head_eager(rough_heatmaps, margin, _debug)
+
+    @torch.no_grad()
+    def _forward_head_eager(self, rough_heatmaps, margin, _debug=None):
         if self.training:
             raise NotImplementedError("CUDA OTPose head implements eval-mode forward; call .eval()")
         _lib.require_cuda(rough_heatmaps)

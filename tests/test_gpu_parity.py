@@ -550,3 +550,22 @@ def test_head_batch_consistency_full_batch():
     # the Gram partial sums are grouped by a batch-dependent chunking, so across
     # batch sizes the result agrees to (network-amplified) rounding, not bitwise
     assert rel(outb[0], out1[0]) < 2e-4
+
+
+def test_head_cuda_graph_replay_matches_eager():
+    """OTPose(cuda_graph=True): forward_head replayed from a captured CUDA graph (static input /
+    output buffers) is bit-identical to the eager launches, also after the inputs change."""
+    b, h, w = 2, 24, 16
+    model, sd = build_head(h, w, "fp16")
+    eager = [t.clone() for t in model.forward_head(syn.synth_rough_heatmaps(b, 17, h, w, seed=1).cuda(),
+                                                   syn.synth_margin(b, seed=2).cuda())]
+    model.cuda_graph = True
+    for seed in (5, 1):      # capture on other data, then replay on the first input
+        rough = syn.synth_rough_heatmaps(b, 17, h, w, seed=seed).cuda()
+        margin = syn.synth_margin(b, seed=seed + 1).cuda()
+        outs = model.forward_head(rough, margin)
+    assert len(model._graphs) == 1
+    for n, o, e in zip(NAMES, outs, eager):
+        assert torch.equal(o, e), n
+    model.load_state_dict(sd)          # parameters replaced -> graphs dropped
+    assert len(model._graphs) == 0
