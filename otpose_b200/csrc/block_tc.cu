@@ -9,24 +9,26 @@
 //             tiles re-read as MN-major operands, accumulated in TMEM over the CTA's
 //             whole token chunk                                                 (tensor)
 //             vn (16-bit, already in operand layout) is written for tc_apply.
+//             Warp-specialised (compute / MMA issuer / halo warps): block_tc_front.cuh.
 //   fold      softmax + W_eff = softmax(S) W_v, emitted as an operand image (block_fold.cuh).
 //   tc_apply  o = W_eff vn + b_eff : one M128 x N144 x K144 UMMA per tile, stored
 //             token-major 16-bit == the reference's scramble buffer.
-//   tc_back   proj UMMA -> u = skip + s_a(.) -> LN2 (registers) -> 6 x { W1 chunk UMMA
-//             (N96, double-buffered in TMEM so chunk j+1 runs under chunk j's GELU) ->
-//             bias + GELU -> H tile -> W2 chunk UMMA accumulating in TMEM } -> y = u + s_m(.)
+//   tc_back   proj UMMA -> u = skip + s_a(.) -> LN2 (registers) -> 9 x { W1 chunk UMMA (N64) ->
+//             GELU -> H tile -> W2 chunk UMMA accumulating in TMEM } -> y = u + s_m(.)
+//             Persistent, warp-specialised (TMA producer / MMA issuer / 16 epilogue warps):
+//             block_tc_back.cuh.
 //
 // fp32 is kept for the residual stream, all LayerNorm statistics, the Gram accumulation,
 // softmax and every epilogue; only UMMA operands are 16-bit (template F16: false =
 // bfloat16, true = IEEE half -- same speed, 8x finer rounding; every operand here is
 // O(1)..O(100), far inside the half range).  The affine part of LN_q/LN_k/LN_v/LN2 is
 // folded into the following GEMM's weights and bias when the weights are packed, so the
-// staged operands are plain (x - mean) * rstd.
+// staged operands are plain (x - mean) * rstd; b_p and b_1 ride in the MMAs against a ones
+// column of the activation tile.
 //
-// Thread map of the 384-thread CTAs: warp w -> TMEM lane quarter q4 = w % 4 (a hardware
-// rule of tcgen05.ld), token = 32*q4 + lane, and channel third = w / 4 (48 channels =
-// six 16-byte operand chunks), so a thread's registers, its LayerNorm partial sums and
-// its TMEM columns all refer to the same (token, channel-third).
+// TMEM lane rule: warp w reads lanes 32*(w%4).., so a thread's token is 32*(w%4) + lane and the
+// warps sharing a lane quarter split the accumulator columns (thirds of 48 in tc_front, quarters
+// of 36 in tc_back, halves of 72 in tc_apply).
 #include "block_common.cuh"
 #include "block_fold.cuh"
 #include "tc_common.cuh"
@@ -37,7 +39,6 @@ using namespace tc;
 namespace {
 constexpr int kC = 136, kHS = 68, kKP = 144;
 constexpr int kTM = 128;        // tokens per tile == UMMA M
-constexpr int kTcThreads = 384;
 constexpr int kApplyThreads = 256;
 constexpr uint32_t kCS = 128;                 // byte stride between 8-element K chunks
 constexpr uint32_t kRS144 = (kKP / 8) * 128;  // byte stride between 8-row groups, K = 144
@@ -48,9 +49,6 @@ constexpr uint32_t kRS96 = (kNH / 8) * 128;        // 768  (row-group stride of 
 constexpr uint32_t kW1c = (kNH / 8) * kRS144;      // 13824  [48][144]
 constexpr uint32_t kW2c = (kKP / 8) * kRS96;       // 13824  [144][48]
 constexpr uint32_t kHTile = (kTM / 8) * kRS96;     // 12288  [128][48]
-constexpr int kXLD = 140;   // fp32 staging row stride; 136 staged tokens [s*ob-4, s*ob+132)
-constexpr int kXOff = 3;    // staged index of input token s*ob-1 (first tap of output token ob)
-constexpr int kNI = 130;    // tokens the tile's taps touch
 
 // ---- packed tensor-core weights of one block (bytes) ----
 struct TcPack {
@@ -199,298 +197,6 @@ __device__ __forceinline__ uint32_t tcol(uint32_t base, int q4, int col) {
   return base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)col;
 }
 
-// ------------------------------------------------------------------ tc_front
-struct FrontVec {  // small fp32 parameters staged in shared memory
-  float ln1w[kC], ln1b[kC];
-  float4 dw[3][kC];          // depthwise taps of q, k, v
-  float bq[kKP], bk[kKP];    // folded biases
-  float part[2][3][kTM];     // per-third partial (sum, sum of squares) per token
-  float parte[2][3][2];      // same for the two halo tokens 128, 129
-};
-
-template <bool F16>
-__global__ void __launch_bounds__(kTcThreads, 1)
-tc_front_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__restrict__ bqp,
-                const float *__restrict__ bkp, const float *__restrict__ x, float *__restrict__ gram_part,
-                uint8_t *__restrict__ vn_img, int T, int Tout, int stride, int tiles, int tiles_per_chunk,
-                int nchunk, float qscale) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  float *xs = reinterpret_cast<float *>(smem);  // [136][140] fp32 staging, later the Wk image
-  uint8_t *aq = smem + kC * kXLD * 4;
-  uint8_t *ak = aq + kTile144;
-  uint8_t *wq = ak + kTile144;
-  FrontVec *V = reinterpret_cast<FrontVec *>(wq + kW144);
-  __shared__ uint64_t bar_mma, bar_gram;
-  __shared__ uint32_t tmem_slot;
-
-  const TcIds id = tc_ids();
-  const int b = blockIdx.y, chunk = blockIdx.x;
-  constexpr TcPack L = tc_pack_layout();
-
-  cp_async_block(wq, tcw + L.wq, kW144, kTcThreads);
-  cp_async_commit();
-  for (int c = threadIdx.x; c < kC; c += kTcThreads) {
-    V->ln1w[c] = P.ln1_w[c];
-    V->ln1b[c] = P.ln1_b[c];
-    V->dw[0][c] = make_float4(P.dwq[3 * c], P.dwq[3 * c + 1], P.dwq[3 * c + 2], 0.f);
-    V->dw[1][c] = make_float4(P.dwk[3 * c], P.dwk[3 * c + 1], P.dwk[3 * c + 2], 0.f);
-    V->dw[2][c] = make_float4(P.dwv[3 * c], P.dwv[3 * c + 1], P.dwv[3 * c + 2], 0.f);
-  }
-  for (int c = threadIdx.x; c < kKP; c += kTcThreads) {
-    V->bq[c] = bqp[c];
-    V->bk[c] = bkp[c];
-  }
-  if (threadIdx.x == 0) {
-    mbar_init(&bar_mma, 1);
-    mbar_init(&bar_gram, 1);
-    fence_mbar_init();
-  }
-  if (id.warp == 0) tmem_alloc(&tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tm = tmem_slot;
-  const uint32_t t_q = tm, t_k = tm + 144, t_g0 = tm + 288, t_g1 = tm + 368;
-  constexpr uint32_t kFmt = F16 ? 0u : 1u;
-  const uint32_t idesc_qk = make_idesc_16(kKP, false, false, kFmt);
-  const uint32_t idesc_gram = make_idesc_16(80, true, true, kFmt);
-  uint32_t ph_mma = 0, ph_gram = 0;
-  bool gram_pending = false;
-
-  const float *xb = x + (size_t)b * kC * T;
-  const int c_lo = id.third * 48, c_hi = min(kC, c_lo + 48);
-  const int tile_begin = chunk * tiles_per_chunk;
-  const int tile_end = min(tiles, tile_begin + tiles_per_chunk);
-  const int ntok = kTM / stride;
-  const bool vec_ok = (T & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-  float *xsh = xs + kXOff;   // xsh[c*kXLD + i] = input token (s*ob - 1 + i)
-
-  for (int tile = tile_begin; tile < tile_end; ++tile) {
-    const int t0 = tile * kTM;
-    const int nvalid = min(kTM, Tout - t0);
-    uint8_t *vn_tile = vn_img + ((size_t)b * tiles + tile) * kTile144;
-    for (int round = 0; round < stride; ++round) {
-      const int ob = t0 + round * ntok;    // first output token of this round
-      const int ib = stride * ob - 1;      // input token of its first tap
-      const int ab = stride * ob - 4;      // first staged token (16-byte aligned row offset)
-      // ---- stage the fp32 input tile: asynchronous copies, everything in flight at once ----
-      if (vec_ok) {
-        for (int e = threadIdx.x; e < kC * 34; e += kTcThreads) {
-          const int c = e / 34, q = e % 34, tk = ab + 4 * q;
-          float *dst = xs + c * kXLD + 4 * q;
-          if (tk >= 0 && tk + 3 < T) cp_async16(dst, xb + (size_t)c * T + tk);
-          else *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      } else {
-        for (int e = threadIdx.x; e < kC * 136; e += kTcThreads) {
-          const int c = e / 136, i = e % 136, tk = ab + i;
-          float *dst = xs + c * kXLD + i;
-          if (tk >= 0 && tk < T) cp_async4(dst, xb + (size_t)c * T + tk);
-          else *dst = 0.f;
-        }
-      }
-      cp_async_commit();
-      cp_async_wait<0>();
-      __syncthreads();
-      // ---- LN1 over channels per staged token (two-pass, fp32) ----
-      const bool has_e = id.tok < kNI - kTM;   // this thread also covers halo token 128 + tok
-      const int extra = kTM + id.tok;
-      {
-        float s0 = 0.f, s1 = 0.f;
-        for (int c = c_lo; c < c_hi; ++c) {
-          s0 += xsh[c * kXLD + id.tok];
-          if (has_e) s1 += xsh[c * kXLD + extra];
-        }
-        V->part[0][id.third][id.tok] = s0;
-        if (has_e) V->parte[0][id.third][id.tok] = s1;
-      }
-      __syncthreads();
-      const float mu0 = (V->part[0][0][id.tok] + V->part[0][1][id.tok] + V->part[0][2][id.tok]) * (1.0f / kC);
-      const float mu1 = has_e ? (V->parte[0][0][id.tok] + V->parte[0][1][id.tok] + V->parte[0][2][id.tok]) * (1.0f / kC)
-                              : 0.f;
-      {
-        float s0 = 0.f, s1 = 0.f;
-        for (int c = c_lo; c < c_hi; ++c) {
-          const float d = xsh[c * kXLD + id.tok] - mu0;
-          s0 = fmaf(d, d, s0);
-          if (has_e) {
-            const float e = xsh[c * kXLD + extra] - mu1;
-            s1 = fmaf(e, e, s1);
-          }
-        }
-        V->part[1][id.third][id.tok] = s0;
-        if (has_e) V->parte[1][id.third][id.tok] = s1;
-      }
-      __syncthreads();
-      {
-        const float r0 = 1.0f / sqrtf((V->part[1][0][id.tok] + V->part[1][1][id.tok] + V->part[1][2][id.tok]) *
-                                          (1.0f / kC) + 1e-5f);
-        const bool v0 = (ib + id.tok >= 0) && (ib + id.tok < T);
-        float r1 = 0.f;
-        bool v1 = false;
-        if (has_e) {
-          r1 = 1.0f / sqrtf((V->parte[1][0][id.tok] + V->parte[1][1][id.tok] + V->parte[1][2][id.tok]) * (1.0f / kC) +
-                            1e-5f);
-          v1 = (ib + extra >= 0) && (ib + extra < T);
-        }
-        for (int c = c_lo; c < c_hi; ++c) {
-          const float w = V->ln1w[c], bb = V->ln1b[c];
-          float *p0 = xsh + c * kXLD + id.tok;
-          *p0 = v0 ? fmaf((*p0 - mu0) * r0, w, bb) : 0.f;   // zero == conv zero padding
-          if (has_e) {
-            float *p1 = xsh + c * kXLD + extra;
-            *p1 = v1 ? fmaf((*p1 - mu1) * r1, w, bb) : 0.f;
-          }
-        }
-      }
-      __syncthreads();
-      // ---- q, k, v in turn: depthwise conv (kept in registers) -> statistics -> (d-mean)*rstd ----
-      const bool active = id.tok < ntok;
-      const int xi = stride * id.tok;
-      const int row = round * ntok + id.tok;
-#pragma unroll 1
-      for (int m = 0; m < 3; ++m) {
-        float d[48];
-        float s = 0.f, ss = 0.f;
-        if (active) {
-#pragma unroll
-          for (int i = 0; i < 48; ++i) {
-            const int c = c_lo + i;
-            float v = 0.f;
-            if (c < kC) {
-              const float *xr = xsh + c * kXLD + xi;
-              const float4 w = V->dw[m][c];
-              v = fmaf(w.z, xr[2], fmaf(w.y, xr[1], w.x * xr[0]));
-            }
-            d[i] = v;
-            s += v;
-            ss = fmaf(v, v, ss);
-          }
-        }
-        V->part[0][id.third][id.tok] = s;
-        V->part[1][id.third][id.tok] = ss;
-        __syncthreads();
-        const float mean = (V->part[0][0][id.tok] + V->part[0][1][id.tok] + V->part[0][2][id.tok]) * (1.0f / kC);
-        const float var = fmaxf((V->part[1][0][id.tok] + V->part[1][1][id.tok] + V->part[1][2][id.tok]) * (1.0f / kC) -
-                                    mean * mean, 0.f);
-        const float rstd = 1.0f / sqrtf(var + 1e-5f);
-        // the previous tile's Gram UMMAs still read aq/ak: wait before overwriting them
-        if (m == 0 && gram_pending) {
-          mbar_wait(&bar_gram, ph_gram);
-          ph_gram ^= 1;
-          gram_pending = false;
-        }
-        if (active) {
-          uint8_t *dst = (m == 0 ? aq : (m == 1 ? ak : vn_tile)) + cm_offset(row, c_lo, kRS144, kCS);
-#pragma unroll
-          for (int g = 0; g < 6; ++g) {
-            float o8[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) o8[e] = (c_lo + g * 8 + e < kC) ? (d[g * 8 + e] - mean) * rstd : 0.f;
-            *reinterpret_cast<uint4 *>(dst + g * kCS) = pack16x8<F16>(o8);
-          }
-        }
-        __syncthreads();   // part[] is rewritten by the next matrix; xs by the next round / Wk
-      }
-    }
-    // ---- Wk image -> the (now dead) staging region; q and k projections on the tensor cores ----
-    cp_async_block(reinterpret_cast<uint8_t *>(xs), tcw + L.wk, kW144, kTcThreads);
-    cp_async_commit();
-    cp_async_wait<0>();
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      tc_fence_after();
-      const uint32_t a_q = smem_u32(aq), a_k = smem_u32(ak), w_q = smem_u32(wq), w_k = smem_u32(xs);
-#pragma unroll
-      for (int s = 0; s < kKP / 16; ++s)
-        umma_bf16(t_q, make_desc(a_q + s * 2 * kCS, kCS, kRS144), make_desc(w_q + s * 2 * kCS, kCS, kRS144),
-                  idesc_qk, s > 0);
-#pragma unroll
-      for (int s = 0; s < kKP / 16; ++s)
-        umma_bf16(t_k, make_desc(a_k + s * 2 * kCS, kCS, kRS144), make_desc(w_k + s * 2 * kCS, kCS, kRS144),
-                  idesc_qk, s > 0);
-      umma_commit(&bar_mma);
-    }
-    mbar_wait(&bar_mma, ph_mma);
-    ph_mma ^= 1;
-    tc_fence_after();
-    // ---- epilogue: + bias, * 1/sqrt(hs) for q, 16 bit, back into aq / ak as [token][channel] ----
-    {
-      const bool live = id.tok < nvalid;   // padded tokens must not reach the Gram
-      const int col = id.third * 48;
-      const uint32_t off = cm_offset(id.tok, col, kRS144, kCS);
-      float v[48];
-      tmem_ld48(tcol(t_q, id.q4, col), v);
-#pragma unroll
-      for (int g = 0; g < 6; ++g) {
-        float o8[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o8[e] = live ? (v[g * 8 + e] + V->bq[col + g * 8 + e]) * qscale : 0.f;
-        *reinterpret_cast<uint4 *>(aq + off + g * kCS) = pack16x8<F16>(o8);
-      }
-      tmem_ld48(tcol(t_k, id.q4, col), v);
-#pragma unroll
-      for (int g = 0; g < 6; ++g) {
-        float o8[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o8[e] = live ? v[g * 8 + e] + V->bk[col + g * 8 + e] : 0.f;
-        *reinterpret_cast<uint4 *>(ak + off + g * kCS) = pack16x8<F16>(o8);
-      }
-    }
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    // ---- channel Gram over this tile's tokens: MN-major views of the q / k tiles ----
-    if (threadIdx.x == 0) {
-      tc_fence_after();
-      const uint32_t a_q = smem_u32(aq), a_k = smem_u32(ak);
-      const bool first = tile == tile_begin;
-#pragma unroll
-      for (int s = 0; s < kTM / 16; ++s) {
-        const uint32_t ko = s * 2 * kRS144;
-        // head 0: rows = q channels 0..127, cols = k channels 0..79
-        umma_bf16(t_g0, make_desc(a_q + ko, kRS144, kCS), make_desc(a_k + ko, kRS144, kCS), idesc_gram,
-                  !(first && s == 0));
-        // head 1: rows = q channels 8..135, cols = k channels 64..143
-        umma_bf16(t_g1, make_desc(a_q + ko + kCS, kRS144, kCS), make_desc(a_k + ko + 8 * kCS, kRS144, kCS),
-                  idesc_gram, !(first && s == 0));
-      }
-      umma_commit(&bar_gram);
-    }
-    gram_pending = true;
-  }
-  if (gram_pending) {
-    mbar_wait(&bar_gram, ph_gram);
-    ph_gram ^= 1;
-  }
-  tc_fence_after();
-  // ---- flush the partial Gram: TMEM lane == q channel (row), column == k channel ----
-  if (id.third < 2) {
-    float *gp = gram_part + (size_t)(b * nchunk + chunk) * kC * kHS;
-    const int row_ch = id.third ? 8 + id.tok : id.tok;          // q channel of this lane
-    const bool row_ok = id.third ? (row_ch >= kHS && row_ch < kC) : (row_ch < kHS);
-    const int col0 = id.third ? 4 : 0;                            // first useful column
-    const uint32_t tg = id.third ? t_g1 : t_g0;
-#pragma unroll 1
-    for (int g = 0; g < 10; ++g) {
-      float v[8];
-      tmem_ld8(tcol(tg, id.q4, g * 8), v);
-      if (row_ok) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int j = g * 8 + e - col0;
-          if (j >= 0 && j < kHS) gp[(size_t)row_ch * kHS + j] = v[e];
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (id.warp == 0) tmem_dealloc(tm, 512);
-}
-
 // ------------------------------------------------------------------ tc_apply
 template <bool F16>
 __global__ void __launch_bounds__(kApplyThreads, 2)
@@ -616,10 +322,8 @@ void pack_image(bool f16, const float *src, int ld, int row0, int col0, int rv, 
     pack_image_kernel<false><<<ceil_div(rp * cp, 256), 256, 0, st>>>(src, ld, row0, col0, rv, cv, colscale, dst, rp, cp);
 }
 
-constexpr size_t kFrontSmem = (size_t)kC * kXLD * 4 + 2 * kTile144 + kW144 + sizeof(FrontVec);
 constexpr size_t kApplySmem = (size_t)kTile144 + kW144;
 constexpr size_t kBackSmem = (size_t)2 * kTile144 + kW144 + kBackTH * kHTile + kBackSlots * kW1c + sizeof(BackVec);
-static_assert(kFrontSmem <= 226 * 1024, "tc_front shared memory");
 static_assert(kBackSmem + 1024 <= 227 * 1024, "tc_back shared memory");
 
 template <bool F16>
@@ -642,8 +346,8 @@ int forward_tc_t(const void *packed_fp32, const void *packed_tc, const float *x,
   unsigned short *obuf = reinterpret_cast<unsigned short *>(ws + W.obuf);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(tc_front_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFrontSmem);
-    cudaFuncSetAttribute(tc_front1_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFront1Smem);
+    cudaFuncSetAttribute(tc_front1_kernel<F16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFront1Smem);
+    cudaFuncSetAttribute(tc_front1_kernel<F16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFront1Smem);
     cudaFuncSetAttribute(tc_apply_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kApplySmem);
     cudaFuncSetAttribute(tc_back_kernel<F16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBackSmem);
     cudaFuncSetAttribute(tc_back_kernel<F16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBackSmem);
@@ -652,12 +356,11 @@ int forward_tc_t(const void *packed_fp32, const void *packed_tc, const float *x,
   {
     LaunchScope ls(K_TC_FRONT, st);
     if (stride == 1)
-      tc_front1_kernel<F16><<<dim3(W.nchunk, b), kFrThreads, kFront1Smem, st>>>(
-          P, tcw, bqp, bkp, x, gram, vn, t, W.tiles, W.tiles_per_chunk, W.nchunk, 1.0f / sqrtf((float)kHS));
+      tc_front1_kernel<F16, false><<<dim3(W.nchunk, b), kFrThreads, kFront1Smem, st>>>(
+          P, tcw, bqp, bkp, x, gram, vn, t, W.tout, W.tiles, W.tiles_per_chunk, W.nchunk, 1.0f / sqrtf((float)kHS));
     else
-      tc_front_kernel<F16><<<dim3(W.nchunk, b), kTcThreads, kFrontSmem, st>>>(
-          P, tcw, bqp, bkp, x, gram, vn, t, W.tout, stride, W.tiles, W.tiles_per_chunk, W.nchunk,
-          1.0f / sqrtf((float)kHS));
+      tc_front1_kernel<F16, true><<<dim3(W.nchunk, b), kFrThreads, kFront1Smem, st>>>(
+          P, tcw, bqp, bkp, x, gram, vn, t, W.tout, W.tiles, W.tiles_per_chunk, W.nchunk, 1.0f / sqrtf((float)kHS));
   }
   {
     LaunchScope ls(K_BLOCK_FOLD, st);

@@ -1,7 +1,6 @@
-// tc_front (stride-1 blocks): LN1 -> {dw_q, dw_k, dw_v} -> {LN_q, LN_k, LN_v} -> q / k projections ->
-// per-CTA partial channel Gram, of one TransformerBlock (model/blocks.py:264-268, 400-440).
-// Included by block_tc.cu inside its anonymous namespace.  The stride-2 branch blocks keep the
-// generic tc_front_kernel.
+// tc_front: LN1 -> {dw_q, dw_k, dw_v} -> {LN_q, LN_k, LN_v} -> q / k projections -> per-CTA partial
+// channel Gram, of one TransformerBlock (model/blocks.py:264-268, 400-440), stride-1 stem blocks and
+// (template S2) stride-2 branch blocks.  Included by block_tc.cu inside its anonymous namespace.
 //
 // One warp-specialised CTA per (clip, token chunk), 448 threads:
 //   warps 0-11  COMPUTE: thread (q4, lane, third) owns token 32*q4 + lane and 48 channels.  The
@@ -20,7 +19,7 @@ struct Front1Vec {
   float ln1w[kC], ln1b[kC];
   float4 dw[3][kC];          // depthwise taps of q, k, v
   float bq[kKP], bk[kKP];    // folded biases
-  float part[2][2][3][kTM];  // [parity of the pass][mean | M2 or sum | sumsq][third][token]
+  float part[2][4][3][kTM];  // [parity of the pass][mean | M2 or sum | sumsq (| odd input: mean | M2)][third][token]
 };
 struct Front1Bars {
   uint64_t wfull;            // TMA arrival of Wq | Wk
@@ -46,11 +45,17 @@ __device__ __forceinline__ void unpack8(const uint4 &p, float (&f)[8]) {
   }
 }
 
-template <bool F16>
+// S2 = the stride-2 branch blocks (depthwise convs with stride 2: output token j reads inputs 2j-1,
+// 2j, 2j+1).  Thread = OUTPUT token: LN1 of its even input stays in registers (fp32), LN1 of its odd
+// input goes to the shared tile (row j = input 2j+1: its own right tap and token j+1's left tap), so
+// the tile is the same size as for stride 1; only a left halo row (input 2*t0-1) is needed.  The two
+// input tokens are loaded at the start of the tile (no register room to prefetch them a tile ahead).
+template <bool F16, bool S2>
 __global__ void __launch_bounds__(kFrThreads, 1)
 tc_front1_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__restrict__ bqp,
                  const float *__restrict__ bkp, const float *__restrict__ x, float *__restrict__ gram_part,
-                 uint8_t *__restrict__ vn_img, int T, int tiles, int tiles_per_chunk, int nchunk, float qscale) {
+                 uint8_t *__restrict__ vn_img, int T, int Tout, int tiles, int tiles_per_chunk, int nchunk,
+                 float qscale) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *aq = smem;
   uint8_t *ak = aq + kTile144;
@@ -148,8 +153,8 @@ tc_front1_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__re
       if (n >= 2) mbar_wait(&bars.adone, n & 1);   // tile n-2 no longer reads halo[n & 1]
       const int t0 = tile * kTM;
 #pragma unroll 1
-      for (int side = 0; side < 2; ++side) {
-        const int t = side ? t0 + kTM : t0 - 1;
+      for (int side = 0; side < (S2 ? 1 : 2); ++side) {
+        const int t = S2 ? 2 * t0 - 1 : (side ? t0 + kTM : t0 - 1);
         const bool ok = t >= 0 && t < T;
         float v[5];
         float s = 0.f;
@@ -183,24 +188,28 @@ tc_front1_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__re
     const int tok = q4 * 32 + lane;
     const int c_lo = third * 48;
     const int nq = min(48, kC - c_lo);   // valid channels of this third (48, 48, 40)
-    float xr[48];
+    float xr[48];              // stride 1: the token's x, one tile ahead; stride 2: the even input 2j
+    float xo[S2 ? 48 : 1];     // stride 2: the odd input 2j+1
     auto load_x = [&](int tile) {
-      const int t = tile * kTM + tok;
+      const int t = S2 ? 2 * (tile * kTM + tok) : tile * kTM + tok;
       const float *p = xb + (size_t)c_lo * T + t;
 #pragma unroll
       for (int i = 0; i < 48; ++i) {
         xr[i] = (t < T && i < nq) ? __ldg(p) : 0.f;
+        if (S2) xo[i] = (t + 1 < T && i < nq) ? __ldg(p + 1) : 0.f;
         p += T;
       }
     };
-    if (tile_begin < tile_end) load_x(tile_begin);
+    if (!S2 && tile_begin < tile_end) load_x(tile_begin);
     uint32_t n = 0, pp = 0;
     const uint8_t *hrow = hs + tok * kHsRow + c_lo * 2;
     for (int tile = tile_begin; tile < tile_end; ++tile, ++n) {
       const int t0 = tile * kTM;
-      const int nvalid = min(kTM, T - t0);
-      const bool live = tok < nvalid;
+      const int nvalid = min(kTM, Tout - t0);
+      const bool live = tok < nvalid;                             // output token (and its even input) exists
+      const bool live_o = S2 && 2 * (t0 + tok) + 1 < T;           // its odd input exists
       uint8_t *vn_tile = vn_img + ((size_t)b * tiles + tile) * kTile144;
+      if (S2) load_x(tile);
       // ---- LN1 over the token's 136 channels: per-thread (mean, M2), parallel-variance combine ----
       {
         float s = 0.f;
@@ -215,8 +224,45 @@ tc_front1_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__re
         }
         V->part[pp][0][third][tok] = mq;
         V->part[pp][1][third][tok] = m2;
+        if (S2) {
+          float so = 0.f;
+#pragma unroll
+          for (int i = 0; i < 48; ++i) so += xo[i];
+          const float mo = so / (float)nq;
+          float m2o = 0.f;
+#pragma unroll
+          for (int i = 0; i < 48; ++i) {
+            const float d = i < nq ? xo[i] - mo : 0.f;
+            m2o = fmaf(d, d, m2o);
+          }
+          V->part[pp][2][third][tok] = mo;
+          V->part[pp][3][third][tok] = m2o;
+        }
       }
       fr_bar_sync();
+      if (S2) {   // odd input: LN1 -> 16-bit shared row; the even input is normalised in place below (xr := h)
+        const float m0 = V->part[pp][2][0][tok], m1 = V->part[pp][2][1][tok], m2 = V->part[pp][2][2][tok];
+        const float mu = (48.f * (m0 + m1) + 40.f * m2) * (1.0f / kC);
+        const float d0 = m0 - mu, d1 = m1 - mu, d2 = m2 - mu;
+        const float var = (V->part[pp][3][0][tok] + V->part[pp][3][1][tok] + V->part[pp][3][2][tok] +
+                           48.f * (d0 * d0 + d1 * d1) + 40.f * d2 * d2) * (1.0f / kC);
+        const float rstd = 1.0f / sqrtf(var + 1e-5f);
+        uint8_t *dst = hs + tok * kHsRow + c_lo * 2;
+#pragma unroll
+        for (int g = 0; g < 6; ++g) {
+          if (g * 8 < nq) {
+            __half2 h2[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = c_lo + g * 8 + 2 * e;
+              const float a0 = live_o ? fmaf((xo[g * 8 + 2 * e] - mu) * rstd, V->ln1w[c], V->ln1b[c]) : 0.f;
+              const float a1 = live_o ? fmaf((xo[g * 8 + 2 * e + 1] - mu) * rstd, V->ln1w[c + 1], V->ln1b[c + 1]) : 0.f;
+              h2[e] = __floats2half2_rn(a0, a1);
+            }
+            *reinterpret_cast<uint4 *>(dst + g * 16) = *reinterpret_cast<const uint4 *>(h2);
+          }
+        }
+      }
       {
         const float m0 = V->part[pp][0][0][tok], m1 = V->part[pp][0][1][tok], m2 = V->part[pp][0][2][tok];
         const float mu = (48.f * (m0 + m1) + 40.f * m2) * (1.0f / kC);
@@ -235,17 +281,23 @@ tc_front1_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__re
               const int c = c_lo + g * 8 + 2 * e;
               const float a0 = live ? fmaf((xr[g * 8 + 2 * e] - mu) * rstd, V->ln1w[c], V->ln1b[c]) : 0.f;
               const float a1 = live ? fmaf((xr[g * 8 + 2 * e + 1] - mu) * rstd, V->ln1w[c + 1], V->ln1b[c + 1]) : 0.f;
-              h2[e] = __floats2half2_rn(a0, a1);   // zero == the conv's zero padding past the sequence end
+              if (S2) {   // centre tap stays in registers (fp32)
+                xr[g * 8 + 2 * e] = a0;
+                xr[g * 8 + 2 * e + 1] = a1;
+              } else {
+                h2[e] = __floats2half2_rn(a0, a1);   // zero == the conv's zero padding past the sequence end
+              }
             }
-            *reinterpret_cast<uint4 *>(dst + g * 16) = *reinterpret_cast<const uint4 *>(h2);
+            if (!S2) *reinterpret_cast<uint4 *>(dst + g * 16) = *reinterpret_cast<const uint4 *>(h2);
           }
         }
       }
-      if (tile + 1 < tile_end) load_x(tile + 1);   // next tile's x: in flight for the rest of this tile
+      if (!S2 && tile + 1 < tile_end) load_x(tile + 1);   // next tile's x: in flight for the rest of this tile
       fr_bar_sync();
       mbar_wait(&bars.halo_full[n & 1], (n >> 1) & 1);
       const uint8_t *lrow = tok == 0 ? halo + ((n & 1) * 2 + 0) * kHsRow + c_lo * 2 : hrow - kHsRow;
-      const uint8_t *rrow = tok == kTM - 1 ? halo + ((n & 1) * 2 + 1) * kHsRow + c_lo * 2 : hrow + kHsRow;
+      const uint8_t *rrow = S2 ? hrow   // stride 2: the right tap is this token's own odd input
+                               : (tok == kTM - 1 ? halo + ((n & 1) * 2 + 1) * kHsRow + c_lo * 2 : hrow + kHsRow);
       // ---- q, k, v in turn: depthwise conv (registers) -> statistics -> (d - mean) * rstd -> operand tile ----
 #pragma unroll 1
       for (int m = 0; m < 3; ++m) {
@@ -256,7 +308,12 @@ tc_front1_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__re
           if (g * 8 < nq) {
             float l8[8], c8[8], r8[8];
             unpack8(*reinterpret_cast<const uint4 *>(lrow + g * 16), l8);
-            unpack8(*reinterpret_cast<const uint4 *>(hrow + g * 16), c8);
+            if (S2) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) c8[e] = xr[g * 8 + e];
+            } else {
+              unpack8(*reinterpret_cast<const uint4 *>(hrow + g * 16), c8);
+            }
             unpack8(*reinterpret_cast<const uint4 *>(rrow + g * 16), r8);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
