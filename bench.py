@@ -319,13 +319,15 @@ def run_b200(args):
     # per-kernel table / roofline: a second pass of the same K steps with the library's CUDA events
     # around every launch (2 events x ~190 launches per step cost ~7 % of the step, hence separate)
     graph_mode = model.cuda_graph
-    model.cuda_graph = False                       # per-kernel events need the individual launches
+    model.cuda_graph = False                       # per-kernel events need the individual launches,
+    model.overlap_branches = False                 # one after the other (no side-stream overlap)
     lib.otp_profile_enable(1)
     launches1 = lib.otp_launch_count()
     ms_profiled = timed(step_resident, args.steps)
     if graph_mode:   # the timed region replayed these same kernels as graph nodes: count them here
         launches = lib.otp_launch_count() - launches1
     model.cuda_graph = graph_mode
+    model.overlap_branches = True
     prof = _lib.profile_read()
     lib.otp_profile_enable(0)
     for _ in range(2):

@@ -77,6 +77,7 @@ class OTPose(nn.Module):
         self.cuda_graph = bool(cuda_graph)   # opt-in: replay forward_head from a captured CUDA graph
         self._graphs = {}
         self._side_streams = {}
+        self.overlap_branches = True    # def_fuse on a side stream, concurrent with the flow encoder
         if extra['FINAL_CONV_KERNEL'] != 1:
             raise NotImplementedError("final_layer kernels are built for FINAL_CONV_KERNEL = 1")
         if backbone is not None:
@@ -270,11 +271,15 @@ class OTPose(nn.Module):
             side = self._side_streams.get(dev.index)
             if side is None:
                 side = self._side_streams[dev.index] = torch.cuda.Stream(device=dev)
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
+            if self.overlap_branches:
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    def_heatmaps = self.def_fuse(total_b)
+                    cat[:, 2 * j:].copy_(def_heatmaps)
+                def_heatmaps.record_stream(main)
+            else:
                 def_heatmaps = self.def_fuse(total_b)
                 cat[:, 2 * j:].copy_(def_heatmaps)
-            def_heatmaps.record_stream(main)
             ctx = self.flow_encoder(total_b)[0]                                  # (B, J, T)
             x1 = torch.empty((b, c8, t), **f32)
             x2 = torch.empty((b, c8, t), **f32)
@@ -295,7 +300,8 @@ class OTPose(nn.Module):
                     cat.data_ptr() + 4 * i * j * t, 3 * j * t, st), "otp_pyramid_conv1x1")
                 del s0, s1, s2
             del x1, x2
-            main.wait_stream(side)
+            if self.overlap_branches:
+                main.wait_stream(side)
             trans = self.offset_mask_combine_conv(cat)
             if _debug is not None:
                 _debug.update(cat=cat, trans=trans, def_heatmaps=def_heatmaps)
