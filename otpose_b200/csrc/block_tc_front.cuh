@@ -335,6 +335,7 @@ tc_front1_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__re
         const float var = fmaxf((V->part[pp][1][0][tok] + V->part[pp][1][1][tok] + V->part[pp][1][2][tok]) * (1.0f / kC) -
                                     mean * mean, 0.f);
         const float rstd = 1.0f / sqrtf(var + 1e-5f);
+        const float nmr = -mean * rstd;   // (d - mean) * rstd as one FMA
         pp ^= 1;
         // the previous tile's Gram UMMAs still read aq / ak: wait before overwriting them
         if (m == 0 && n > 0) mbar_wait(&bars.gdone, (n - 1) & 1);
@@ -343,7 +344,7 @@ tc_front1_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__re
         for (int g = 0; g < 6; ++g) {
           float o8[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o8[e] = (g * 8 + e < nq) ? (d[g * 8 + e] - mean) * rstd : 0.f;
+          for (int e = 0; e < 8; ++e) o8[e] = (g * 8 + e < nq) ? fmaf(d[g * 8 + e], rstd, nmr) : 0.f;
           *reinterpret_cast<uint4 *>(dst + g * kCS) = pack16x8<F16>(o8);
         }
         if (m < 2) {

@@ -72,7 +72,10 @@ conv_tc_kernel(const float *__restrict__ x, long long x_bs, const float *__restr
   const int P = H * W;
   const int cg = S.cpad / 8, wch = W / 8;
   const int halo = k == 3 ? wch : 0;   // chunks staged before the tile's first pixel
-  const uint32_t ncols = S.npad <= 16 ? 32 : (S.npad <= 32 ? 64 : (S.npad <= 64 ? 128 : 256));   // two accumulators
+  // two accumulators (UMMAs of the next tile issued before this tile's epilogue) up to 64 output
+  // channels; wider convs keep one accumulator so that 3-4 CTAs per SM still fit the 512 TMEM columns
+  const bool dbl = S.npad <= 64;
+  const uint32_t ncols = S.npad <= 16 ? 32 : (S.npad <= 32 ? 64 : 128);
 
   // weights: contiguous 16-bit operand image (K-major rows of taps*cpad)
   for (uint32_t o = threadIdx.x * 16; o < S.w_bytes; o += kCtThreads * 16) cp_async16(wsm + o, wimg + o);
@@ -210,11 +213,11 @@ conv_tc_kernel(const float *__restrict__ x, long long x_bs, const float *__restr
   }
   for (; g < total; g += stepg, ++n) {
     const int b = g / tiles, p0 = (g % tiles) * kCtTM;
-    const uint32_t acc = tm + (n & 1) * S.npad;
+    const uint32_t acc = dbl ? tm + (n & 1) * S.npad : tm;
     mbar_wait(&bar, phase);   // tile n: accumulator ready, staged copies free
     phase ^= 1;
     tc_fence_after();
-    if (g + stepg < total) {
+    if (dbl && g + stepg < total) {
       stage_and_issue(tm + ((n + 1) & 1) * S.npad);   // tile n+1 (v[] holds its data)
       if (g + 2 * stepg < total) load_tile(g + 2 * stepg);
     }
@@ -241,6 +244,10 @@ conv_tc_kernel(const float *__restrict__ x, long long x_bs, const float *__restr
       }
     }
     tc_fence_before();   // this accumulator is rewritten by the UMMAs issued after the next __syncthreads
+    if (!dbl && g + stepg < total) {
+      stage_and_issue(tm);
+      if (g + 2 * stepg < total) load_tile(g + 2 * stepg);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -337,7 +344,7 @@ extern "C" int otp_conv2d_tc(const float *x, long long x_bstride, const float *x
       x, x_bstride, x_add, x_add_bstride, pk, bias, residual, residual_bstride, y, y_bstride, b, cin, h, w, cout, k, \
       relu, tiles)
   // resident CTAs that shared memory and the 512 TMEM columns (two accumulators per CTA) allow
-  const int tcols = S.npad <= 16 ? 32 : (S.npad <= 32 ? 64 : (S.npad <= 64 ? 128 : 256));
+  const int tcols = S.npad <= 16 ? 32 : (S.npad <= 32 ? 64 : 128);
   const int max_cta = max(1, min((int)((227 * 1024) / (S.smem + 2048)), 512 / tcols));
   const int per_thread = ceil_div(S.cpad * (int)S.s_chunks, kCtThreads);
   const bool f16 = precision == OTP_PREC_FP16;
