@@ -360,7 +360,7 @@ def run_b200(args):
         roofline = {"kernel": top, "bound": tk["bound"], "achieved": tk["achieved"], "peak": peaks[tk["bound"]],
                     "unit": tk["unit"], "frac": tk["frac"], "traffic": traffic,
                     "peak_source": f"{peaks['source']} ({'sustained bf16' if tk['bound'] == 'tensor' else 'copy'})",
-                    "share_of_step": round(tk["ms_per_step"] / (ms_profiled / args.steps), 4),
+                    "share_of_step": round(tk["ms_per_step"] / sum(k["ms_per_step"] for k in kernels.values()), 4),
                     "timing": "CUDA events around every launch of this kernel in a separate pass of the same "
                               f"{args.steps} steps ({ms_profiled / args.steps:.3f} ms/step with events)"}
         line = {"metric": METRIC, "value": b * world * args.steps / (ms * 1e-3), "unit": "clips/s",
