@@ -163,6 +163,37 @@ class OTPose(nn.Module):
         rough_heatmaps = self.rough_pose_estimation_net(x)
         return self.forward_head(rough_heatmaps, kwargs["margin"])
 
+    # ------------------------------------------------------------------ a0: HRNet.final_layer boundary
+    @torch.no_grad()
+    def forward_from_features(self, features, margin, weight=None, bias=None):
+        """Optional wider boundary: take the backbone's last 48-channel feature map
+        ``y_list[0]`` (frames*B, 48, H, W) and apply ``HRNet.final_layer`` (1x1 conv 48 -> J,
+        model/HRNet.py:108-114, 150) here, through ``otp_conv2d`` in fp32, before the head.
+        ``weight`` / ``bias`` default to ``self.rough_pose_estimation_net.final_layer`` when a
+        backbone with that attribute is attached.  Returns the reference 7-tuple; element 1 is the
+        rough heat maps computed here."""
+        _lib.require_cuda(features)
+        if weight is None:
+            fl = self.rough_pose_estimation_net.final_layer
+            weight, bias = fl.weight, fl.bias
+        n, cin, h, w = features.shape
+        j = weight.shape[0]
+        if tuple(weight.shape[1:]) != (cin, 1, 1):
+            raise NotImplementedError("final_layer: built for FINAL_CONV_KERNEL = 1")
+        feats = features if (features.dtype == torch.float32 and features.is_contiguous()) else \
+            features.float().contiguous()
+        rough = torch.empty((n, j, h, w), dtype=torch.float32, device=feats.device)
+        if n:
+            lib = _lib.load()
+            wt = weight.detach().float().contiguous()
+            bs = (bias.detach().float().contiguous() if bias is not None
+                  else torch.zeros(j, dtype=torch.float32, device=feats.device))
+            with torch.cuda.device(feats.device):
+                _lib.check(lib.otp_conv2d(_lib.dptr(feats), cin * h * w, None, 0, _lib.dptr(wt), _lib.dptr(bs), None, 0,
+                                          rough.data_ptr(), j * h * w, n, cin, h, w, j, 1, 1, 0,
+                                          _lib.stream_ptr(feats.device)), "otp_conv2d")
+        return self.forward_head(rough, margin)
+
     # ------------------------------------------------------------------ CUDA graph replay (opt-in)
     def invalidate_graphs(self):
         """Drop captured graphs (call after changing parameters in place; ``load_state_dict``, ``.to()``

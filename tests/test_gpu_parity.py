@@ -569,3 +569,23 @@ def test_head_cuda_graph_replay_matches_eager():
         assert torch.equal(o, e), n
     model.load_state_dict(sd)          # parameters replaced -> graphs dropped
     assert len(model._graphs) == 0
+
+
+def test_head_from_backbone_features_a0():
+    """HRNet.final_layer (1x1 conv 48 -> 17, model/HRNet.py:108-114, 150) applied inside
+    the drop-in, against the oracle run on the reference-order ATen conv of the same features."""
+    import torch.nn.functional as F
+    b, h, w = 1, 24, 16
+    model, sd = build_head(h, w, "fp32")
+    g = torch.Generator().manual_seed(1235)
+    feats = torch.randn(5 * b, 48, h, w, generator=g)
+    wt = torch.randn(17, 48, 1, 1, generator=g) / 48 ** 0.5
+    bias = torch.randn(17, generator=g) * 0.1
+    margin = syn.synth_margin(b)
+    rough_ref = F.conv2d(feats, wt, bias)
+    ref = ho.head_forward(sd, rough_ref, margin)
+    outs = model.forward_from_features(feats.cuda(), margin.cuda(), wt.cuda(), bias.cuda())
+    assert rel(outs[1], rough_ref) < 1e-5
+    for n, o, r in zip(NAMES, outs, ref):
+        if n != "rough_heatmaps":
+            assert rel(o, r) < FP32_TOL, n
