@@ -187,6 +187,17 @@ int otp_pyramid_conv1x1(const float *s0, const float *s1, const float *s2, int b
                         int t1, int t2, const float *weight, const float *bias, int cout,
                         float *out, long long out_bstride, otp_stream_t stream);
 
+/* a6, 16-bit tensor-core variant (t % 8 == 0, cout <= 32): the upsampled / stacked operand tile is
+ * built in shared memory in 16 bit and contracted by tcgen05 UMMAs with the packed weight image
+ * (otp_pyramid_conv1x1_tc_pack of the (cout, 3c) fp32 weight for the same precision). */
+int otp_pyramid_conv1x1_tc_supported(int c, int t, int cout);
+size_t otp_pyramid_conv1x1_tc_pack_bytes(int c);
+int otp_pyramid_conv1x1_tc_pack(const float *weight, int c, int cout, int precision, void *packed,
+                                size_t packed_bytes, otp_stream_t stream);
+int otp_pyramid_conv1x1_tc(const float *s0, const float *s1, const float *s2, int b, int c, int t,
+                           const void *packed, const float *bias, int cout, float *out,
+                           long long out_bstride, int precision, otp_stream_t stream);
+
 /* ---------------------------------------------------------------------------
  * a7/a8  small-channel Conv2d (stride 1, square kernel k in {1,3}, dilation d,
  * padding d*(k/2)), replaces the nn.Conv2d (+folded eval BatchNorm + ReLU) calls

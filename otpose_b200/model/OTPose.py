@@ -77,6 +77,7 @@ class OTPose(nn.Module):
         self.cuda_graph = bool(cuda_graph)   # opt-in: replay forward_head from a captured CUDA graph
         self._graphs = {}
         self._side_streams = {}
+        self._pyramid_cache = {}
         self.overlap_branches = True    # def_fuse on a side stream, concurrent with the flow encoder
         if extra['FINAL_CONV_KERNEL'] != 1:
             raise NotImplementedError("final_layer kernels are built for FINAL_CONV_KERNEL = 1")
@@ -162,6 +163,21 @@ class OTPose(nn.Module):
         x = torch.cat(x.split(3, dim=1), 0)
         rough_heatmaps = self.rough_pose_estimation_net(x)
         return self.forward_head(rough_heatmaps, kwargs["margin"])
+
+    def _pyramid_packed(self, i, fl, prec):
+        """16-bit operand image of final_layer{i+1}.weight (cached; rebuilt when the parameter changes)."""
+        key = (fl.weight.data_ptr(), fl.weight._version, prec)
+        ent = self._pyramid_cache.get(i)
+        if ent is None or ent[0] != key:
+            lib = _lib.load()
+            j, c3 = fl.weight.shape[0], fl.weight.shape[1]
+            nbytes = lib.otp_pyramid_conv1x1_tc_pack_bytes(c3 // 3)
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=fl.weight.device)
+            _lib.check(lib.otp_pyramid_conv1x1_tc_pack(_lib.dptr(fl.weight.detach().view(j, c3).contiguous()), c3 // 3, j,
+                                                       prec, buf.data_ptr(), nbytes,
+                                                       _lib.stream_ptr(fl.weight.device)), "otp_pyramid_conv1x1_tc_pack")
+            ent = self._pyramid_cache[i] = (key, buf)
+        return ent[1]
 
     # ------------------------------------------------------------------ a0: HRNet.final_layer boundary
     @torch.no_grad()
@@ -325,10 +341,18 @@ class OTPose(nn.Module):
             for i, (enc, fl, xin) in enumerate(((self.temporal_encoder1, self.final_layer1, x1),
                                                 (self.temporal_encoder2, self.final_layer2, x2))):
                 s0, s1, s2 = enc.forward_tokens(xin)
-                _lib.check(lib.otp_pyramid_conv1x1(
-                    _lib.dptr(s0), _lib.dptr(s1), _lib.dptr(s2), b, c8, t, s1.shape[-1], s2.shape[-1],
-                    _lib.dptr(fl.weight.detach().view(j, 3 * c8)), _lib.dptr(fl.bias.detach()), j,
-                    cat.data_ptr() + 4 * i * j * t, 3 * j * t, st), "otp_pyramid_conv1x1")
+                pprec = _lib.precision_code(self.precision)
+                if (pprec != _lib.PREC_FP32 and s1.shape[-1] * 2 == t and s2.shape[-1] * 4 == t
+                        and lib.otp_pyramid_conv1x1_tc_supported(c8, t, j)):
+                    _lib.check(lib.otp_pyramid_conv1x1_tc(
+                        _lib.dptr(s0), _lib.dptr(s1), _lib.dptr(s2), b, c8, t, self._pyramid_packed(i, fl, pprec).data_ptr(),
+                        _lib.dptr(fl.bias.detach()), j, cat.data_ptr() + 4 * i * j * t, 3 * j * t, pprec, st),
+                        "otp_pyramid_conv1x1_tc")
+                else:
+                    _lib.check(lib.otp_pyramid_conv1x1(
+                        _lib.dptr(s0), _lib.dptr(s1), _lib.dptr(s2), b, c8, t, s1.shape[-1], s2.shape[-1],
+                        _lib.dptr(fl.weight.detach().view(j, 3 * c8)), _lib.dptr(fl.bias.detach()), j,
+                        cat.data_ptr() + 4 * i * j * t, 3 * j * t, st), "otp_pyramid_conv1x1")
                 del s0, s1, s2
             del x1, x2
             if self.overlap_branches:
