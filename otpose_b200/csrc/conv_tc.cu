@@ -22,7 +22,8 @@ namespace otp {
 using namespace tc;
 namespace {
 
-constexpr int kCtThreads = 128;
+constexpr int kCtMaxThreads = 256;   // CTAs of 128 threads (small convs: more CTAs per SM) or 256 threads
+                                     // (two warps per TMEM lane quarter split the output channels)
 constexpr int kCtTM = 128;   // pixels per tile
 
 struct ConvTcShape {
@@ -55,7 +56,7 @@ __device__ __forceinline__ uint32_t tmem_slot_after_sync(const uint32_t *slot) {
   return *slot;
 }
 
-template <bool F16, int kU, int kMinCta>
+template <bool F16, int kU, int kMinCta, int kCtThreads>
 __global__ void __launch_bounds__(kCtThreads, kMinCta)
 conv_tc_kernel(const float *__restrict__ x, long long x_bs, const float *__restrict__ x_add, long long xa_bs,
                const uint8_t *__restrict__ wimg, const float *__restrict__ bias, const float *__restrict__ residual,
@@ -223,13 +224,14 @@ conv_tc_kernel(const float *__restrict__ x, long long x_bs, const float *__restr
     }
     // ---- epilogue of tile n: lane == pixel, column == output channel ----
     {
-      const int p = p0 + warp * 32 + lane;
+      const int q4 = warp & 3, hw = warp >> 2;   // lane quarter; which 16-column groups (even / odd)
+      const int p = p0 + q4 * 32 + lane;
       const bool live = p < P;
-      float *yp = y + (size_t)b * y_bs + p;
-      const float *rp = residual ? residual + (size_t)b * r_bs + p : nullptr;
-      for (int n0 = 0; n0 < S.npad; n0 += 16) {
+      for (int n0 = hw * 16; n0 < S.npad; n0 += 16 * (kCtThreads / 128)) {
         float a16[16];
-        tmem_ld16(acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0, a16);
+        tmem_ld16(acc + ((uint32_t)(q4 * 32) << 16) + (uint32_t)n0, a16);
+        float *yp = y + (size_t)b * y_bs + (size_t)n0 * P + p;
+        const float *rp = residual ? residual + (size_t)b * r_bs + (size_t)n0 * P + p : nullptr;
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           if (n0 + e < cout && live) {
@@ -268,8 +270,8 @@ __global__ void conv_tc_pack_kernel(const float *__restrict__ w, int cin, int co
 bool conv_tc_supported(int cin, int cout, int h, int w, int k) {
   if ((k != 1 && k != 3) || w % 8 != 0 || cin > 96 || cout > 96) return false;
   const ConvTcShape s = conv_tc_shape(cin, cout, k, w);
-  // every staged item of a tile lives in the registers of one thread slot (<= 12 per thread)
-  return s.smem <= 100 * 1024 && ceil_div(s.cpad * (int)s.s_chunks, kCtThreads) <= 12;
+  // every staged item of a tile lives in the registers of one thread slot (<= 6 per thread)
+  return s.smem <= 100 * 1024 && ceil_div(s.cpad * (int)s.s_chunks, kCtMaxThreads) <= 6;
 }
 
 }  // namespace
@@ -326,36 +328,38 @@ extern "C" int otp_conv2d_tc(const float *x, long long x_bstride, const float *x
   static bool attr_done = false;
   if (!attr_done) {
     const int lim = 100 * 1024;
-    cudaFuncSetAttribute(conv_tc_kernel<true, 3, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    cudaFuncSetAttribute(conv_tc_kernel<false, 3, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    cudaFuncSetAttribute(conv_tc_kernel<true, 5, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    cudaFuncSetAttribute(conv_tc_kernel<false, 5, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    cudaFuncSetAttribute(conv_tc_kernel<true, 9, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    cudaFuncSetAttribute(conv_tc_kernel<false, 9, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    cudaFuncSetAttribute(conv_tc_kernel<true, 12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    cudaFuncSetAttribute(conv_tc_kernel<false, 12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+#define OTP_CONV_ATTR(U, M, NT)                                                                                   \
+  cudaFuncSetAttribute(conv_tc_kernel<true, U, M, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);         \
+  cudaFuncSetAttribute(conv_tc_kernel<false, U, M, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)
+    OTP_CONV_ATTR(3, 6, 128);
+    OTP_CONV_ATTR(5, 4, 128);
+    OTP_CONV_ATTR(5, 2, 256);
+    OTP_CONV_ATTR(6, 2, 256);
+#undef OTP_CONV_ATTR
     attr_done = true;
   }
   LaunchScope ls(K_CONV2D, st);
   const uint8_t *pk = static_cast<const uint8_t *>(packed);
   const int total = tiles * b;
-#define OTP_CONV_TC(F16, U, MINCTA)                                                                              \
-  conv_tc_kernel<F16, U, MINCTA><<<min(total, num_sms() * min(MINCTA, max_cta)), kCtThreads, S.smem, st>>>(           \
+#define OTP_CONV_TC(F16, U, MINCTA, NT)                                                                          \
+  conv_tc_kernel<F16, U, MINCTA, NT><<<min(total, num_sms() * min(MINCTA, max_cta)), NT, S.smem, st>>>(               \
       x, x_bstride, x_add, x_add_bstride, pk, bias, residual, residual_bstride, y, y_bstride, b, cin, h, w, cout, k, \
       relu, tiles)
   // resident CTAs that shared memory and the 512 TMEM columns (two accumulators per CTA) allow
   const int tcols = S.npad <= 16 ? 32 : (S.npad <= 32 ? 64 : 128);
   const int max_cta = max(1, min((int)((227 * 1024) / (S.smem + 2048)), 512 / tcols));
-  const int per_thread = ceil_div(S.cpad * (int)S.s_chunks, kCtThreads);
+  // small convs (<= 5 staged items per thread at 128 threads): 128-thread CTAs, 4-6 per SM;
+  // larger ones: 256-thread CTAs (half the per-tile latency chain), 2 per SM
+  const int items = S.cpad * (int)S.s_chunks;
   const bool f16 = precision == OTP_PREC_FP16;
-  if (per_thread <= 3) {
-    if (f16) OTP_CONV_TC(true, 3, 6); else OTP_CONV_TC(false, 3, 6);
-  } else if (per_thread <= 5) {
-    if (f16) OTP_CONV_TC(true, 5, 4); else OTP_CONV_TC(false, 5, 4);
-  } else if (per_thread <= 9) {
-    if (f16) OTP_CONV_TC(true, 9, 3); else OTP_CONV_TC(false, 9, 3);
+  if (items <= 3 * 128) {
+    if (f16) OTP_CONV_TC(true, 3, 6, 128); else OTP_CONV_TC(false, 3, 6, 128);
+  } else if (items <= 5 * 128) {
+    if (f16) OTP_CONV_TC(true, 5, 4, 128); else OTP_CONV_TC(false, 5, 4, 128);
+  } else if (items <= 5 * 256) {
+    if (f16) OTP_CONV_TC(true, 5, 2, 256); else OTP_CONV_TC(false, 5, 2, 256);
   } else {
-    if (f16) OTP_CONV_TC(true, 12, 2); else OTP_CONV_TC(false, 12, 2);
+    if (f16) OTP_CONV_TC(true, 6, 2, 256); else OTP_CONV_TC(false, 6, 2, 256);
   }
 #undef OTP_CONV_TC
   return check_launch("conv_tc_kernel");
