@@ -237,8 +237,13 @@ tc_apply_kernel(const uint8_t *__restrict__ vn_img, const uint8_t *__restrict__ 
   }
   mbar_wait(&bar, 0);
   tc_fence_after();
-  // token-major store obuf[b][head][token][68] (16 bit) == the reference's scramble buffer
+  // token-major store obuf[b][head][token][68] (16 bit) == the reference's scramble buffer.  A tile's
+  // rows of one head are ONE contiguous block of nvalid * 136 bytes in global memory: the tile is
+  // assembled in shared memory (over the dead operand tile) and leaves with two bulk (TMA) stores
+  // instead of 18 scattered 8-byte stores per thread (each warp store touched 32 separate sectors).
   unsigned short *ob = obuf + (size_t)b * kC * Tout;
+  const bool bulk = ((Tout | nvalid) & 1) == 0;   // 16-byte size / alignment of the blocks
+  unsigned short *stage = reinterpret_cast<unsigned short *>(a);   // [2 heads][128 tokens][68]
 #pragma unroll 1
   for (int g = 0; g < 9; ++g) {
     const int col = half * 72 + g * 8;
@@ -253,9 +258,26 @@ tc_apply_kernel(const uint8_t *__restrict__ vn_img, const uint8_t *__restrict__ 
           uint2 pk;
           pk.x = pack16x2<F16>(v[4 * q] + sb[n4], v[4 * q + 1] + sb[n4 + 1]);
           pk.y = pack16x2<F16>(v[4 * q + 2] + sb[n4 + 2], v[4 * q + 3] + sb[n4 + 3]);
-          *reinterpret_cast<uint2 *>(ob + ((size_t)h * Tout + t0 + tok) * kHS + cp) = pk;
+          if (bulk)
+            *reinterpret_cast<uint2 *>(stage + (h * kTM + tok) * kHS + cp) = pk;
+          else
+            *reinterpret_cast<uint2 *>(ob + ((size_t)h * Tout + t0 + tok) * kHS + cp) = pk;
         }
       }
+    }
+  }
+  if (bulk) {
+    fence_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t bytes = (uint32_t)nvalid * kHS * 2;
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(ob + ((size_t)h * Tout + t0) * kHS),
+                     "r"(smem_u32(stage + h * kTM * kHS)), "r"(bytes)
+                     : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the shared tile has been read
     }
   }
   tc_fence_before();
