@@ -327,18 +327,44 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__rest
       {
         const float *xr = x + ((size_t)b * kC + cq) * T + (S2 ? 2 * tt : tt);
         const bool has_l = S2 && tt > 0, has_r = S2 && (2 * tt + 1 < T);
+        if (!S2) {
 #pragma unroll
-        for (int i = 0; i < kCQ; ++i) {
-          float sk = 0.f;
-          if (cq + i < kC && live) {
-            sk = __ldg(xr);
-            if (S2) {   // MaxPool1d(3, 2, 1)
-              if (has_l) sk = fmaxf(sk, __ldg(xr - 1));
-              if (has_r) sk = fmaxf(sk, __ldg(xr + 1));
-            }
+          for (int i = 0; i < kCQ; ++i) {
+            u[i] = (cq + i < kC && live) ? __ldg(xr) : 0.f;
+            xr += T;
           }
-          u[i] = sk;
-          xr += T;
+        } else {
+          // MaxPool1d(3, 2, 1) over inputs 2t-1, 2t, 2t+1.  Two explicit phases so that every load of
+          // a phase is in flight at once within the register budget (a load whose result is consumed
+          // at once would serialise on the memory latency): the 36 left taps, then the (2t, 2t+1)
+          // pairs in batches of 9.
+          const bool pair_ok = (T & 1) == 0;   // (2t, 2t+1) is one aligned 8-byte load
+          const float *xl = xr;
+#pragma unroll
+          for (int i = 0; i < kCQ; ++i) {
+            u[i] = (cq + i < kC && live && has_l) ? __ldg(xl - 1) : -3.402823466e38f;
+            xl += T;
+          }
+#pragma unroll
+          for (int i0 = 0; i0 < kCQ; i0 += 9) {
+            float2 ab[9];
+#pragma unroll
+            for (int e = 0; e < 9; ++e) {
+              const float *p = xr + (size_t)(i0 + e) * T;
+              ab[e] = make_float2(0.f, -3.402823466e38f);
+              if (cq + i0 + e < kC && live) {
+                if (pair_ok) {
+                  ab[e] = __ldg(reinterpret_cast<const float2 *>(p));
+                } else {
+                  ab[e].x = __ldg(p);
+                  if (has_r) ab[e].y = __ldg(p + 1);
+                }
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 9; ++e)
+              u[i0 + e] = (cq + i0 + e < kC && live) ? fmaxf(u[i0 + e], fmaxf(ab[e].x, ab[e].y)) : 0.f;
+          }
         }
       }
       tr(1);

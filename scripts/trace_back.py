@@ -18,7 +18,8 @@ from otpose_b200.utils import synthetic as syn  # noqa: E402
 
 b = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 t = int(sys.argv[2]) if len(sys.argv) > 2 else 6912
-blk = TransformerBlock(136, 2, n_ds_strides=(1, 1), proj_pdrop=0.1, path_pdrop=0.1)
+stride = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+blk = TransformerBlock(136, 2, n_ds_strides=(stride, stride), proj_pdrop=0.1, path_pdrop=0.1)
 blk.load_state_dict(syn.fill_state_dict({k: v.shape for k, v in blk.state_dict().items()}, seed=3))
 blk = blk.cuda().eval()
 x = torch.from_numpy(np.random.default_rng(0).standard_normal((b, 136, t)).astype(np.float32)).cuda()
