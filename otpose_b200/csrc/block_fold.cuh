@@ -39,7 +39,7 @@ block_fold_kernel(const float *__restrict__ wv, const float *__restrict__ bv,
   const float *gp = gram_part + (size_t)b * nchunk * C * HS + (size_t)n0 * HS;
   for (int e = threadIdx.x; e < NB * HS; e += kFoldThreads) {
     float s = 0.f;
-#pragma unroll 4
+#pragma unroll 8
     for (int ch = 0; ch < nchunk; ++ch) s += __ldg(gp + (size_t)ch * C * HS + e);  // fixed order
     S[(e / HS) * LDS + e % HS] = s;
   }
@@ -68,8 +68,8 @@ block_fold_kernel(const float *__restrict__ wv, const float *__restrict__ bv,
     for (int i = 0; i < NB; ++i) acc[i] = 0.f;
     if (c < C) {
       const float *wp = wv + (size_t)(h * HS) * C + c;
-#pragma unroll 8
-      for (int j = 0; j < HS; ++j) {
+#pragma unroll
+      for (int j = 0; j < HS; ++j) {   // fully unrolled: all HS loads of W_v in flight at once
         const float w = __ldg(wp + (size_t)j * C);
 #pragma unroll
         for (int i = 0; i < NB; ++i) acc[i] = fmaf(S[i * LDS + j], w, acc[i]);
