@@ -151,14 +151,15 @@ def profile_read():
 
 
 class _WorkspacePool:
-    """One growing scratch buffer per (device, tag); kernels are stream-ordered so
-    consecutive calls on the same stream can share it."""
+    """One growing scratch buffer per (device, stream, tag); kernels are stream-ordered so
+    consecutive calls on the same stream can share it, and branches running concurrently on
+    different streams (the two temporal encoders) never do."""
 
     def __init__(self):
         self._bufs = {}
 
     def get(self, nbytes: int, device, tag: str = "ws") -> torch.Tensor:
-        key = (torch.device(device).index, tag)
+        key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream, tag)
         buf = self._bufs.get(key)
         if buf is None or buf.numel() < nbytes:
             buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)

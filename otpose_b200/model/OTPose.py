@@ -79,6 +79,7 @@ class OTPose(nn.Module):
         self._side_streams = {}
         self._pyramid_cache = {}
         self.overlap_branches = True    # def_fuse on a side stream, concurrent with the flow encoder
+        self.overlap_encoders = True    # temporal_encoder2 on the side stream, concurrent with temporal_encoder1
         if extra['FINAL_CONV_KERNEL'] != 1:
             raise NotImplementedError("final_layer kernels are built for FINAL_CONV_KERNEL = 1")
         if backbone is not None:
@@ -338,25 +339,36 @@ class OTPose(nn.Module):
                 _lib.dptr(pe1, allow_none=True), _lib.dptr(pe2, allow_none=True), ps1, frames, b, j, t,
                 x1.data_ptr(), x2.data_ptr(), intersection.data_ptr(), prev_b.data_ptr(), st),
                 "otp_fusion_stack_frames")
-            for i, (enc, fl, xin) in enumerate(((self.temporal_encoder1, self.final_layer1, x1),
-                                                (self.temporal_encoder2, self.final_layer2, x2))):
+            pprec = _lib.precision_code(self.precision)
+
+            def encode(i, enc, fl, xin):
+                stq = _lib.stream_ptr(dev)
                 s0, s1, s2 = enc.forward_tokens(xin)
-                pprec = _lib.precision_code(self.precision)
                 if (pprec != _lib.PREC_FP32 and s1.shape[-1] * 2 == t and s2.shape[-1] * 4 == t
                         and lib.otp_pyramid_conv1x1_tc_supported(c8, t, j)):
                     _lib.check(lib.otp_pyramid_conv1x1_tc(
                         _lib.dptr(s0), _lib.dptr(s1), _lib.dptr(s2), b, c8, t, self._pyramid_packed(i, fl, pprec).data_ptr(),
-                        _lib.dptr(fl.bias.detach()), j, cat.data_ptr() + 4 * i * j * t, 3 * j * t, pprec, st),
+                        _lib.dptr(fl.bias.detach()), j, cat.data_ptr() + 4 * i * j * t, 3 * j * t, pprec, stq),
                         "otp_pyramid_conv1x1_tc")
                 else:
                     _lib.check(lib.otp_pyramid_conv1x1(
                         _lib.dptr(s0), _lib.dptr(s1), _lib.dptr(s2), b, c8, t, s1.shape[-1], s2.shape[-1],
                         _lib.dptr(fl.weight.detach().view(j, 3 * c8)), _lib.dptr(fl.bias.detach()), j,
-                        cat.data_ptr() + 4 * i * j * t, 3 * j * t, st), "otp_pyramid_conv1x1")
-                del s0, s1, s2
-            del x1, x2
+                        cat.data_ptr() + 4 * i * j * t, 3 * j * t, stq), "otp_pyramid_conv1x1")
+
+            # the two temporal encoders are independent: encoder 2 (and its pyramid conv) runs on the side
+            # stream, so the ramp / tail of every persistent kernel of one is filled by CTAs of the other
+            both = self.overlap_branches and self.overlap_encoders
+            if both:
+                side.wait_stream(main)                      # x2 is ready
+                with torch.cuda.stream(side):
+                    encode(1, self.temporal_encoder2, self.final_layer2, x2)
+            encode(0, self.temporal_encoder1, self.final_layer1, x1)
+            if not both:
+                encode(1, self.temporal_encoder2, self.final_layer2, x2)
             if self.overlap_branches:
                 main.wait_stream(side)
+            del x1, x2                                       # x2 stays allocated until the side stream has joined
             trans = self.offset_mask_combine_conv(cat)
             if _debug is not None:
                 _debug.update(cat=cat, trans=trans, def_heatmaps=def_heatmaps)
