@@ -56,8 +56,9 @@ struct BackBars {
   uint64_t lnfull;       // epilogue -> control: LN2(u) tile staged (16 warp arrivals)
   uint64_t pfull;        // proj accumulator ready
   uint64_t thfull[kBackTH];   // hidden accumulator t_h[s] ready
-  uint64_t hbfull[kBackTH];   // epilogue -> control: GELU tile hbuf[s] staged (16 warp arrivals)
-  uint64_t hbfree[kBackTH];   // W2 chunk MMA done: hbuf[s] reusable; a tile's last one = y accumulator ready
+  uint64_t hbfull[kBackTH];   // epilogue -> control: GELU tile hbuf[s] staged (8 warp arrivals: the chunk's group)
+  uint64_t hbfree[kBackTH];   // W2 chunk MMA done: hbuf[s] reusable
+  uint64_t yfull;             // a tile's last W2 chunk MMA done: y accumulator complete (one phase per tile)
   uint64_t wfull[kBackSlots];    // TMA arrival of a ring slot
   uint64_t wempty[kBackSlots];   // the MMAs reading a ring slot are done
   uint64_t wpfull;       // TMA arrival of Wp
@@ -147,10 +148,11 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__rest
     mbar_init(&bars.lnfull, kBackEpi / 32);
     mbar_init(&bars.pfull, 1);
     mbar_init(&bars.wpfull, 1);
+    mbar_init(&bars.yfull, 1);
 #pragma unroll
     for (int i = 0; i < kBackTH; ++i) {
       mbar_init(&bars.thfull[i], 1);
-      mbar_init(&bars.hbfull[i], kBackEpi / 32);
+      mbar_init(&bars.hbfull[i], kBackEpi / 64);
       mbar_init(&bars.hbfree[i], 1);
     }
 #pragma unroll
@@ -259,6 +261,7 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__rest
                      (j > 0 || s > 0));
         release_chunk();
         commit_elect(&bars.hbfree[c % kBackTH]);
+        if (j == kNChunk - 1) commit_elect(&bars.yfull);
         if (j + 3 < kNChunk) mma1(c + 3);   // t_h[c%3] was drained by GELU(chunk c) before hbfull[c%3]
         if (j == kNChunk - 2 && it + 1 < ntile) proj(it + 1);   // its out2 tile is published at chunk 6;
                                                                 // E1 of this tile has left t_p (lnfull above)
@@ -445,33 +448,41 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__rest
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.lnfull);
       tr(5);
-      // ---- MLP epilogue: GELU(hidden chunk j) -> 16-bit H tile, 16 columns per thread ----
+      // ---- MLP epilogue: GELU(hidden chunk) -> 16-bit H tile.  The 16 warps form two groups of 8 that
+      //      take ALTERNATE chunks (32 of the 64 hidden columns per thread): the chain of one chunk
+      //      (accumulator wait -> tcgen05.ld -> GELU -> shared stores -> proxy fence -> arrive) overlaps
+      //      the other group's chain of the next chunk instead of serialising in the same warps.  A
+      //      group waits on every other phase of thfull / hbfree; that is safe because it has seen chunk
+      //      c-2 (issued after chunk c-3, the previous phase of the same slot) before it waits for c. ----
       const bool has_next = it + 1 < ntile;
 #pragma unroll 1
       for (int j = 0; j < kNChunk; ++j) {
         const int c = c0 + j;
-        const uint32_t par = (c / kBackTH) & 1;
-        mbar_wait(&bars.thfull[c % kBackTH], par);
-        if (c >= kBackTH) mbar_wait(&bars.hbfree[c % kBackTH], par ^ 1);   // W2 chunk c-3 has consumed hbuf[c%3]
-        tc_fence_after();
-        tr(10 + j);
-        float hv[16];
-        tmem_ld16(tcol(t_h + (c % kBackTH) * kNH, q4, quarter * kHQ), hv);
-        uint8_t *dst = hbuf + (c % kBackTH) * kHTile + cm_offset(tok, quarter * kHQ, kRSH, kCS);
+        if ((c & 1) == (quarter & 1)) {
+          const uint32_t par = (c / kBackTH) & 1;
+          mbar_wait(&bars.thfull[c % kBackTH], par);
+          if (c >= kBackTH) mbar_wait(&bars.hbfree[c % kBackTH], par ^ 1);   // W2 chunk c-3 has consumed hbuf[c%3]
+          tc_fence_after();
+          tr(10 + j);
+          const int hcol = (quarter >> 1) * 2 * kHQ;   // 32 hidden columns of this thread
+          float hv[2 * kHQ];
+          tmem_ld32(tcol(t_h + (c % kBackTH) * kNH, q4, hcol), hv);
+          uint8_t *dst = hbuf + (c % kBackTH) * kHTile + cm_offset(tok, hcol, kRSH, kCS);
 #pragma unroll
-        for (int gg = 0; gg < 2; ++gg) {
-          const float *v = hv + gg * 8;
-          uint4 w4;
-          w4.x = gelu_pair<F16>(v[0], v[1]);
-          w4.y = gelu_pair<F16>(v[2], v[3]);
-          w4.z = gelu_pair<F16>(v[4], v[5]);
-          w4.w = gelu_pair<F16>(v[6], v[7]);
-          *reinterpret_cast<uint4 *>(dst + gg * kCS) = w4;
+          for (int gg = 0; gg < 4; ++gg) {
+            const float *v = hv + gg * 8;
+            uint4 w4;
+            w4.x = gelu_pair<F16>(v[0], v[1]);
+            w4.y = gelu_pair<F16>(v[2], v[3]);
+            w4.z = gelu_pair<F16>(v[4], v[5]);
+            w4.w = gelu_pair<F16>(v[6], v[7]);
+            *reinterpret_cast<uint4 *>(dst + gg * kCS) = w4;
+          }
+          fence_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars.hbfull[c % kBackTH]);
         }
-        fence_async_smem();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars.hbfull[c % kBackTH]);
         tr(30 + j);
         if (has_next) {
           const int gn = g + gridDim.x;
@@ -497,7 +508,8 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__rest
       {
         float *yp = y + ((size_t)b * kC + cq) * Tout + tt;
         const int cl = c0 + kNChunk - 1;
-        mbar_wait(&bars.hbfree[cl % kBackTH], (cl / kBackTH) & 1);   // last W2 chunk: y accumulator complete
+        (void)cl;
+        mbar_wait(&bars.yfull, it & 1);   // last W2 chunk of the tile: y accumulator complete
         tc_fence_after();
         tr(50);
         auto piece = [&](const float *v, int i0, int cnt) {
