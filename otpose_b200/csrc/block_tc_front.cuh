@@ -292,7 +292,6 @@ tc_front1_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__re
           }
         }
       }
-      if (!S2 && tile + 1 < tile_end) load_x(tile + 1);   // next tile's x: in flight for the rest of this tile
       fr_bar_sync();
       mbar_wait(&bars.halo_full[n & 1], (n >> 1) & 1);
       const uint8_t *lrow = tok == 0 ? halo + ((n & 1) * 2 + 0) * kHsRow + c_lo * 2 : hrow - kHsRow;
@@ -356,6 +355,9 @@ tc_front1_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__re
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.adone);
+      // next tile's x: issued after the proxy fences of the q and k passes (fence.proxy.async waits for the
+      // thread's pending loads), in flight during the epilogue
+      if (!S2 && tile + 1 < tile_end) load_x(tile + 1);
       // ---- epilogue: + bias, * 1/sqrt(hs) for q, 16 bit, back into aq / ak as [token][channel] ----
       {
         const uint32_t off = cm_offset(tok, c_lo, kRS144, kCS);
