@@ -379,10 +379,12 @@ int forward_tc_t(const void *packed_fp32, const void *packed_tc, const float *x,
     LaunchScope ls(K_TC_FRONT, st);
     if (stride == 1)
       tc_front1_kernel<F16, false><<<dim3(W.nchunk, b), kFrThreads, kFront1Smem, st>>>(
-          P, tcw, bqp, bkp, x, gram, vn, t, W.tout, W.tiles, W.tiles_per_chunk, W.nchunk, 1.0f / sqrtf((float)kHS));
+          P, tcw, bqp, bkp, x, gram, vn, t, W.tout, W.tiles, W.tiles_per_chunk, W.nchunk, 1.0f / sqrtf((float)kHS),
+          g_trace_on);
     else
       tc_front1_kernel<F16, true><<<dim3(W.nchunk, b), kFrThreads, kFront1Smem, st>>>(
-          P, tcw, bqp, bkp, x, gram, vn, t, W.tout, W.tiles, W.tiles_per_chunk, W.nchunk, 1.0f / sqrtf((float)kHS));
+          P, tcw, bqp, bkp, x, gram, vn, t, W.tout, W.tiles, W.tiles_per_chunk, W.nchunk, 1.0f / sqrtf((float)kHS),
+          g_trace_on);
   }
   {
     LaunchScope ls(K_BLOCK_FOLD, st);
@@ -411,7 +413,8 @@ bool block_tc_built() { return true; }
 void block_tc_trace(int on) { g_trace_on = on; }
 int block_tc_trace_read(unsigned long long *out, int n) {
   if (n < 3 * kTraceLen) return OTP_ERR_ARG;
-  cudaError_t e = cudaMemcpyFromSymbol(out, g_back_trace, sizeof(unsigned long long) * 3 * kTraceLen);
+  const int rows = n >= 4 * kTraceLen ? 4 : 3;   // row 3 (tc_front) only for callers that ask for it
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_back_trace, sizeof(unsigned long long) * rows * kTraceLen);
   if (e != cudaSuccess) {
     set_error("block_tc_trace_read: %s", cudaGetErrorString(e));
     return OTP_ERR_CUDA;

@@ -26,7 +26,8 @@
 // Optional phase trace (otp_debug_trace): CTA 0 records (clock64 << 8 | event) for epilogue warp 0
 // (row 0) and the control warp (row 1).
 constexpr int kTraceLen = 2048;
-__device__ unsigned long long g_back_trace[3][kTraceLen];   // epilogue warp 0, control, epilogue warp 15
+__device__ unsigned long long g_back_trace[4][kTraceLen];   // tc_back: epilogue warp 0, control, epilogue warp 15;
+                                                            // row 3: tc_front compute warp 0
 struct Tracer {
   unsigned long long *p;
   int n;

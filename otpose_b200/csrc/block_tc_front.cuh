@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kFrThreads, 1)
 tc_front1_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__restrict__ bqp,
                  const float *__restrict__ bkp, const float *__restrict__ x, float *__restrict__ gram_part,
                  uint8_t *__restrict__ vn_img, int T, int Tout, int tiles, int tiles_per_chunk, int nchunk,
-                 float qscale) {
+                 float qscale, int trace) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *aq = smem;
   uint8_t *ak = aq + kTile144;
@@ -203,12 +203,22 @@ tc_front1_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__re
     if (!S2 && tile_begin < tile_end) load_x(tile_begin);
     uint32_t n = 0, pp = 0;
     const uint8_t *hrow = hs + tok * kHsRow + c_lo * 2;
+    // optional phase trace (build with -DOTP_FRONT_TRACE, then otp_debug_trace / scripts/trace_front.py):
+    // compute warp 0 of CTA (0, 0) -> row 3 of the trace buffer.  Compiled out by default: the kernel sits
+    // at its 128-register ceiling and the tracer's three registers turn into spills.
+#ifdef OTP_FRONT_TRACE
+    Tracer tr{(trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) ? g_back_trace[3] : nullptr, 0};
+#else
+    (void)trace;
+    auto tr = [](int) {};
+#endif
     for (int tile = tile_begin; tile < tile_end; ++tile, ++n) {
       const int t0 = tile * kTM;
       const int nvalid = min(kTM, Tout - t0);
       const bool live = tok < nvalid;                             // output token (and its even input) exists
       const bool live_o = S2 && 2 * (t0 + tok) + 1 < T;           // its odd input exists
       uint8_t *vn_tile = vn_img + ((size_t)b * tiles + tile) * kTile144;
+      tr(0);
       if (S2) load_x(tile);
       // ---- LN1 over the token's 136 channels: per-thread (mean, M2), parallel-variance combine ----
       {
@@ -239,7 +249,9 @@ tc_front1_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__re
           V->part[pp][3][third][tok] = m2o;
         }
       }
+      tr(1);
       fr_bar_sync();
+      tr(2);
       if (S2) {   // odd input: LN1 -> 16-bit shared row; the even input is normalised in place below (xr := h)
         const float m0 = V->part[pp][2][0][tok], m1 = V->part[pp][2][1][tok], m2 = V->part[pp][2][2][tok];
         const float mu = (48.f * (m0 + m1) + 40.f * m2) * (1.0f / kC);
@@ -292,8 +304,11 @@ tc_front1_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__re
           }
         }
       }
+      tr(3);
       fr_bar_sync();
+      tr(4);
       mbar_wait(&bars.halo_full[n & 1], (n >> 1) & 1);
+      tr(5);
       const uint8_t *lrow = tok == 0 ? halo + ((n & 1) * 2 + 0) * kHsRow + c_lo * 2 : hrow - kHsRow;
       const uint8_t *rrow = S2 ? hrow   // stride 2: the right tap is this token's own odd input
                                : (tok == kTM - 1 ? halo + ((n & 1) * 2 + 1) * kHsRow + c_lo * 2 : hrow + kHsRow);
@@ -329,7 +344,9 @@ tc_front1_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__re
         }
         V->part[pp][0][third][tok] = s;
         V->part[pp][1][third][tok] = ss;
+        tr(10 + m);
         fr_bar_sync();
+        tr(20 + m);
         const float mean = (V->part[pp][0][0][tok] + V->part[pp][0][1][tok] + V->part[pp][0][2][tok]) * (1.0f / kC);
         const float var = fmaxf((V->part[pp][1][0][tok] + V->part[pp][1][1][tok] + V->part[pp][1][2][tok]) * (1.0f / kC) -
                                     mean * mean, 0.f);
@@ -338,6 +355,7 @@ tc_front1_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__re
         pp ^= 1;
         // the previous tile's Gram UMMAs still read aq / ak: wait before overwriting them
         if (m == 0 && n > 0) mbar_wait(&bars.gdone, (n - 1) & 1);
+        tr(30 + m);
         uint8_t *dst = (m == 0 ? aq : (m == 1 ? ak : vn_tile)) + cm_offset(tok, c_lo, kRS144, kCS);
 #pragma unroll
         for (int g = 0; g < 6; ++g) {
@@ -352,6 +370,7 @@ tc_front1_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__re
           __syncwarp();
           if (lane == 0) mbar_arrive(m == 0 ? &bars.qfull : &bars.kfull);
         }
+        tr(40 + m);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.adone);
@@ -362,8 +381,10 @@ tc_front1_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__re
       {
         const uint32_t off = cm_offset(tok, c_lo, kRS144, kCS);
         float v[48];
+        tr(50);
         mbar_wait(&bars.qdone, n & 1);
         tc_fence_after();
+        tr(51);
         tmem_ld48(tcol(t_q, q4, c_lo), v);
 #pragma unroll
         for (int g = 0; g < 6; ++g) {
@@ -372,8 +393,10 @@ tc_front1_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__re
           for (int e = 0; e < 8; ++e) o8[e] = live ? (v[g * 8 + e] + V->bq[c_lo + g * 8 + e]) * qscale : 0.f;
           *reinterpret_cast<uint4 *>(aq + off + g * kCS) = pack16x8<F16>(o8);
         }
+        tr(52);
         mbar_wait(&bars.kdone, n & 1);
         tc_fence_after();
+        tr(53);
         tmem_ld48(tcol(t_k, q4, c_lo), v);
 #pragma unroll
         for (int g = 0; g < 6; ++g) {
@@ -383,7 +406,9 @@ tc_front1_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__re
           *reinterpret_cast<uint4 *>(ak + off + g * kCS) = pack16x8<F16>(o8);
         }
       }
+      tr(54);
       fence_async_smem();
+      tr(55);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.gfull);
