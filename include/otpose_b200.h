@@ -140,6 +140,21 @@ int otp_fusion_stack_frames(const float *rough, const int64_t *margin, const flo
                             int frames, int b, int j, int t, float *x1, float *x2,
                             float *intersection, float *prev_b, otp_stream_t stream);
 
+/* a0 + a1 fused (backbone -> head hand-off): HRNet.final_layer -- the 1x1 conv
+ * Cin -> J the backbone ends with (model/HRNet.py:108-114, 150; called at model/OTPose.py:319) --
+ * and the frame sum of model/OTPose.py:324-326 in one pass over the backbone's last feature map.
+ *   features   (frames*B, Cin, H, W), frames ordered cur, prev1, next1, ... (OTPose.py:317-321);
+ *              feat_dtype: OTP_PREC_FP32 / _BF16 / _FP16 element type; channels_last = 0: NCHW
+ *              contiguous (what the reference's backbone returns), 1: NHWC contiguous (a
+ *              channels-last cuDNN backbone); 16-byte aligned, Cin % 8 == 0, Cin <= 64
+ *   weight     (J, Cin) fp32 = final_layer.weight viewed 2-D (FINAL_CONV_KERNEL = 1), bias (J) or NULL
+ *   rough      (frames*B, J, T) fp32 out = the rough_heatmaps OTPose.forward returns
+ *   total_b    (B, J, T), squeezed (B, T) fp32 out, bit-identical to otp_fusion_sum_frames(rough)
+ * fp32 accumulation whatever the element type. */
+int otp_final_layer_fusion_sum(const void *features, int feat_dtype, int channels_last, const float *weight,
+                               const float *bias, int frames, int b, int cin, int joints, int t, float *rough,
+                               float *total_b, float *squeezed, otp_stream_t stream);
+
 /* ---------------------------------------------------------------------------
  * a2-a5  ConvTransformer building blocks, replaces model/blocks.py:95-110
  * (LayerNorm), :264-279 (TransformerBlock.forward), :400-452 (MaskedMHCA.forward),

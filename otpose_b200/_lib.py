@@ -59,6 +59,7 @@ SIGNATURES = {
     "otp_pyramid_conv1x1_tc_pack_bytes": (sz, [i32]),
     "otp_pyramid_conv1x1_tc_pack": (i32, [vp, i32, i32, i32, vp, sz, vp]),
     "otp_pyramid_conv1x1_tc": (i32, [vp, vp, vp, i32, i32, i32, vp, vp, i32, vp, i64, i32, vp]),
+    "otp_final_layer_fusion_sum": (i32, [vp, i32, i32, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
     "otp_conv2d": (i32, [vp, i64, vp, i64, vp, vp, vp, i64, vp, i64, i32, i32, i32, i32, i32, i32, i32,
                          i32, vp]),
     "otp_conv2d_tc_supported": (i32, [i32, i32, i32, i32, i32]),

@@ -183,12 +183,15 @@ class OTPose(nn.Module):
     # ------------------------------------------------------------------ a0: HRNet.final_layer boundary
     @torch.no_grad()
     def forward_from_features(self, features, margin, weight=None, bias=None):
-        """Optional wider boundary: take the backbone's last 48-channel feature map
-        ``y_list[0]`` (frames*B, 48, H, W) and apply ``HRNet.final_layer`` (1x1 conv 48 -> J,
-        model/HRNet.py:108-114, 150) here, through ``otp_conv2d`` in fp32, before the head.
-        ``weight`` / ``bias`` default to ``self.rough_pose_estimation_net.final_layer`` when a
-        backbone with that attribute is attached.  Returns the reference 7-tuple; element 1 is the
-        rough heat maps computed here."""
+        """Wider boundary (the backbone -> head hand-off): take the backbone's last
+        feature map ``y_list[0]`` (frames*B, Cin, H, W) and apply ``HRNet.final_layer`` (1x1 conv Cin -> J,
+        model/HRNet.py:108-114, 150) here.  ``features`` may be fp32 / bf16 / fp16, NCHW-contiguous (what
+        the reference's backbone returns) or ``torch.channels_last`` (a channels-last cuDNN backbone): one
+        kernel (``otp_final_layer_fusion_sum``) reads it once and writes the rough heat maps together with
+        ``total_b`` / ``squeezed`` of model/OTPose.py:324-326, so the head starts without re-reading them.
+        ``weight`` / ``bias`` default to ``self.rough_pose_estimation_net.final_layer`` when a backbone with
+        that attribute is attached.  Returns the reference 7-tuple; element 1 is the rough heat maps
+        computed here (fp32)."""
         _lib.require_cuda(features)
         if weight is None:
             fl = self.rough_pose_estimation_net.final_layer
@@ -197,19 +200,48 @@ class OTPose(nn.Module):
         j = weight.shape[0]
         if tuple(weight.shape[1:]) != (cin, 1, 1):
             raise NotImplementedError("final_layer: built for FINAL_CONV_KERNEL = 1")
-        feats = features if (features.dtype == torch.float32 and features.is_contiguous()) else \
-            features.float().contiguous()
-        rough = torch.empty((n, j, h, w), dtype=torch.float32, device=feats.device)
-        if n:
+        frames = margin.shape[1] + 1
+        if frames not in (3, 5, 7) or n % frames:
+            raise NotImplementedError(f"frame window of {frames} not built (3, 5 or 7)")
+        dcode = {torch.float32: _lib.PREC_FP32, torch.bfloat16: _lib.PREC_BF16, torch.float16: _lib.PREC_FP16}
+        feats = features
+        if feats.dtype not in dcode:
+            feats = feats.float()
+        if feats.is_contiguous():
+            nhwc = 0
+        elif feats.is_contiguous(memory_format=torch.channels_last):
+            nhwc = 1
+        else:
+            feats, nhwc = feats.contiguous(), 0
+        b, t, dev = n // frames, h * w, feats.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        rough = torch.empty((n, j, h, w), **f32)
+        total_b = torch.empty((b, j, h, w), **f32)
+        squeezed = torch.empty((b, 1, h, w), **f32)
+        fused = j == 17 and cin % 8 == 0 and cin <= 64
+        if n and not fused:       # other widths: the generic fp32 conv kernel, then the head from the rough maps
             lib = _lib.load()
+            feats = feats.float().contiguous()
             wt = weight.detach().float().contiguous()
             bs = (bias.detach().float().contiguous() if bias is not None
-                  else torch.zeros(j, dtype=torch.float32, device=feats.device))
-            with torch.cuda.device(feats.device):
-                _lib.check(lib.otp_conv2d(_lib.dptr(feats), cin * h * w, None, 0, _lib.dptr(wt), _lib.dptr(bs), None, 0,
-                                          rough.data_ptr(), j * h * w, n, cin, h, w, j, 1, 1, 0,
-                                          _lib.stream_ptr(feats.device)), "otp_conv2d")
-        return self.forward_head(rough, margin)
+                  else torch.zeros(j, dtype=torch.float32, device=dev))
+            with torch.cuda.device(dev):
+                _lib.check(lib.otp_conv2d(_lib.dptr(feats), cin * t, None, 0, _lib.dptr(wt), _lib.dptr(bs), None, 0,
+                                          rough.data_ptr(), j * t, n, cin, h, w, j, 1, 1, 0, _lib.stream_ptr(dev)),
+                           "otp_conv2d")
+            return self.forward_head(rough, margin)
+        if n:
+            lib = _lib.load()
+            wt = weight.detach().float().reshape(j, cin).contiguous()
+            bs = bias.detach().float().contiguous() if bias is not None else None
+            with torch.cuda.device(dev):
+                _lib.check(lib.otp_final_layer_fusion_sum(
+                    feats.data_ptr(), dcode[feats.dtype], nhwc, _lib.dptr(wt), _lib.dptr(bs, allow_none=True), frames,
+                    b, cin, j, t, rough.data_ptr(), total_b.data_ptr(), squeezed.data_ptr(), _lib.stream_ptr(dev)),
+                    "otp_final_layer_fusion_sum")
+        if self.cuda_graph and not self.training and n:
+            return self.forward_head(rough, margin)      # the captured graph starts from the rough heat maps
+        return self._forward_head_eager(rough, margin, _pre=(total_b, squeezed))
 
     # ------------------------------------------------------------------ CUDA graph replay (opt-in)
     def invalidate_graphs(self):
@@ -273,7 +305,7 @@ class OTPose(nn.Module):
         return self._forward_head_eager(rough_heatmaps, margin, _debug)
 
     @torch.no_grad()
-    def _forward_head_eager(self, rough_heatmaps, margin, _debug=None):
+    def _forward_head_eager(self, rough_heatmaps, margin, _debug=None, _pre=None):
         if self.training:
             raise NotImplementedError("CUDA OTPose head implements eval-mode forward; call .eval()")
         _lib.require_cuda(rough_heatmaps)
@@ -295,8 +327,11 @@ class OTPose(nn.Module):
         margin = margin.to(device=dev, dtype=torch.int64).contiguous()
         f32 = dict(dtype=torch.float32, device=dev)
         c8 = self.temporal_encoding_dim
-        total_b = torch.empty((b, j, h, w), **f32)
-        squeezed = torch.empty((b, 1, h, w), **f32)
+        if _pre is None:
+            total_b = torch.empty((b, j, h, w), **f32)
+            squeezed = torch.empty((b, 1, h, w), **f32)
+        else:                     # forward_from_features computed them together with the rough heat maps
+            total_b, squeezed = _pre
         intersection = torch.empty((b, j, h, w), **f32)
         prev_b = torch.empty((b, j, h, w), **f32)
         out = torch.empty((b, j, h, w), **f32)
@@ -305,8 +340,9 @@ class OTPose(nn.Module):
             return out, rough_heatmaps, intersection, prev_b, ctx, squeezed.expand(b, j, h, w), total_b
         st = _lib.stream_ptr(dev)
         with torch.cuda.device(dev):
-            _lib.check(lib.otp_fusion_sum_frames(_lib.dptr(rough), frames, b, j, t, total_b.data_ptr(),
-                                                 squeezed.data_ptr(), st), "otp_fusion_sum_frames")
+            if _pre is None:
+                _lib.check(lib.otp_fusion_sum_frames(_lib.dptr(rough), frames, b, j, t, total_b.data_ptr(),
+                                                     squeezed.data_ptr(), st), "otp_fusion_sum_frames")
             if getattr(self, "_rsb_precision", None) != self.precision:   # RSB convs follow the head's precision
                 for mod in self.modules():
                     if isinstance(mod, conv_bn_relu):

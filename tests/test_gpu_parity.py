@@ -589,3 +589,70 @@ def test_head_from_backbone_features_a0():
     for n, o, r in zip(NAMES, outs, ref):
         if n != "rough_heatmaps":
             assert rel(o, r) < FP32_TOL, n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,layout,frames", [("fp32", "nchw", 5), ("fp32", "nhwc", 5), ("bf16", "nhwc", 5),
+                                                  ("fp16", "nhwc", 3), ("bf16", "nchw", 7)])
+def test_final_layer_fusion_sum_a0_a1(dtype, layout, frames):
+    """HRNet.final_layer (model/HRNet.py:108-114, 150) + the frame sum of
+    model/OTPose.py:324-326 in one pass over the backbone's feature map, fp32 NCHW (the reference's layout)
+    and 16-bit channels-last (a channels-last backbone).  rough vs the ATen conv of the SAME (rounded)
+    features at 1e-5; total_b / squeezed bit-identical to otp_fusion_sum_frames on the rough maps written;
+    ragged width (H*W not a multiple of the 256-pixel CTA tile)."""
+    import torch.nn.functional as F
+    b, h, w, cin = 3, 23, 19, 48
+    td = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}[dtype]
+    g = torch.Generator().manual_seed(77)
+    feats = torch.randn(frames * b, cin, h, w, generator=g).to(td)
+    wt = torch.randn(17, cin, generator=g) / cin ** 0.5
+    bias = torch.randn(17, generator=g) * 0.1
+    rough_ref = F.conv2d(feats.float(), wt.view(17, cin, 1, 1), bias)
+    dev_feats = feats.cuda()
+    if layout == "nhwc":
+        dev_feats = dev_feats.contiguous(memory_format=torch.channels_last)
+    lib = _lib.load()
+    t = h * w
+    rough = torch.empty((frames * b, 17, h, w), device="cuda")
+    total_b = torch.empty((b, 17, h, w), device="cuda")
+    squeezed = torch.empty((b, 1, h, w), device="cuda")
+    wt_d, bias_d = wt.cuda(), bias.cuda()
+    _lib.check(lib.otp_final_layer_fusion_sum(
+        dev_feats.data_ptr(), _lib.precision_code(dtype), int(layout == "nhwc"), wt_d.data_ptr(),
+        bias_d.data_ptr(), frames, b, cin, 17, t, rough.data_ptr(), total_b.data_ptr(), squeezed.data_ptr(),
+        None), "otp_final_layer_fusion_sum")
+    assert rel(rough, rough_ref) < 1e-5
+    tb2, sq2 = torch.empty_like(total_b), torch.empty_like(squeezed)
+    _lib.check(lib.otp_fusion_sum_frames(rough.data_ptr(), frames, b, 17, t, tb2.data_ptr(), sq2.data_ptr(), None),
+               "otp_fusion_sum_frames")
+    assert torch.equal(total_b, tb2) and torch.equal(squeezed, sq2)
+    # unsupported widths are refused, not mis-computed
+    assert lib.otp_final_layer_fusion_sum(dev_feats.data_ptr(), 0, 0, wt_d.data_ptr(), None, frames, b, 44, 17, t,
+                                          rough.data_ptr(), total_b.data_ptr(), squeezed.data_ptr(), None) == 2
+
+
+@pytest.mark.gpu
+def test_head_from_channels_last_bf16_features():
+    """forward_from_features on a bf16 channels-last feature map (what a channels-last backbone hands over):
+    the whole head against the oracle run on the ATen conv of the same rounded features, fp32 head mode."""
+    import torch.nn.functional as F
+    b, h, w = 2, 24, 16
+    model, sd = build_head(h, w, "fp32")
+    g = torch.Generator().manual_seed(1235)
+    feats = torch.randn(5 * b, 48, h, w, generator=g).to(torch.bfloat16)
+    wt = torch.randn(17, 48, 1, 1, generator=g) / 48 ** 0.5
+    bias = torch.randn(17, generator=g) * 0.1
+    margin = syn.synth_margin(b)
+    rough_ref = F.conv2d(feats.float(), wt, bias)
+    ref = ho.head_forward(sd, rough_ref, margin)
+    outs = model.forward_from_features(feats.cuda().contiguous(memory_format=torch.channels_last), margin.cuda(),
+                                       wt.cuda(), bias.cuda())
+    assert rel(outs[1], rough_ref) < 1e-5
+    for n, o, r in zip(NAMES, outs, ref):
+        if n != "rough_heatmaps":
+            assert rel(o, r) < FP32_TOL, n
+    model.cuda_graph = True            # graph mode: rough maps from the fused kernel, head replayed from the graph
+    outs_g = model.forward_from_features(feats.cuda().contiguous(memory_format=torch.channels_last), margin.cuda(),
+                                         wt.cuda(), bias.cuda())
+    for n, o, e in zip(NAMES, outs_g, outs):
+        assert torch.equal(o, e), n
