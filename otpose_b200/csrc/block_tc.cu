@@ -345,7 +345,7 @@ void pack_image(bool f16, const float *src, int ld, int row0, int col0, int rv, 
 }
 
 constexpr size_t kApplySmem = (size_t)kTile144 + kW144;
-constexpr size_t kBackSmem = (size_t)2 * kTile144 + kW144 + kBackTH * kHTile + kBackSlots * kW1c + sizeof(BackVec);
+constexpr size_t kBackSmem = (size_t)2 * kTile144 + kW144 + kBackHB * kHTile + kBackSlots * kW1c + sizeof(BackVec);
 static_assert(kBackSmem + 1024 <= 227 * 1024, "tc_back shared memory");
 
 template <bool F16>

@@ -2,18 +2,20 @@
 // 441-452) on tcgen05 tensor cores.  Included by block_tc.cu inside its anonymous namespace
 // (uses its tile constants, TcPack and gelu_pair).
 //
-// One persistent, warp-specialised CTA per SM (544 threads, ~204 KB shared memory, 512 TMEM columns):
-//   warp 16            CONTROL (converged warp, single instructions elect-predicated): streams the
-//                      9 + 9 W1 / W2 chunk images with cp.async.bulk (TMA) through a 3-slot ring that
-//                      runs ahead across tile boundaries, issues every tcgen05.mma and signals the
-//                      epilogue through tcgen05.commit -> mbarrier.  Wp stays resident.
+// One persistent, warp-specialised CTA per SM (576 threads, ~218 KB shared memory, 512 TMEM columns):
+//   warp 16            MMA ISSUER (converged warp, single instructions elect-predicated): issues every
+//                      tcgen05.mma and signals the epilogue through tcgen05.commit -> mbarrier.
+//   warp 17            TMA PRODUCER: streams the 9 + 9 W1 / W2 chunk images with cp.async.bulk through a
+//                      4-slot ring that runs ahead across tile boundaries.  Wp stays resident.
 //   warps 0-15         EPILOGUE: thread (q4, lane, quarter) owns token 32*q4 + lane and 36 of the 144
-//                      accumulator columns (16 of the 64 hidden columns of a chunk).
+//                      accumulator columns; in the MLP the warps form two groups (quarter parity) that
+//                      take alternate hidden chunks, 32 of the 64 hidden columns per thread, each group
+//                      with its own GELU tile in shared memory.
 // Software pipeline across tiles: while tile n is in its MLP, the out2 tile of tile n+1 is copied
 // into the other operand buffer, its skip rows are prefetched into L2 and its proj UMMA runs into a
 // second accumulator, so a tile starts with its proj result already in TMEM.  Within the MLP, W1
-// chunk j+2 is issued as soon as GELU(chunk j) has drained its TMEM buffer and the GELU tile is
-// double-buffered: the epilogue warps do not wait for tensor-core round trips in steady state.
+// chunk j+3 is issued as soon as GELU(chunk j) has drained its TMEM buffer and there is one GELU tile
+// per warp group: the epilogue warps do not wait for tensor-core round trips in steady state.
 //
 //  * out2 tile: the (nh, T', hs) 16-bit attention output re-read as (C, T') is a set of 256-byte
 //    runs (128 tokens of one channel), copied with 16-byte cp.async straight into a
@@ -38,8 +40,10 @@ struct Tracer {
 
 constexpr int kBackEpi = 512;                 // epilogue threads (warps 0..15)
 constexpr int kBackThreads = kBackEpi + 64;   // + MMA warp (16) + TMA producer warp (17)
-constexpr int kBackSlots = 3;                 // weight ring slots of kW1c == kW2c bytes
-constexpr int kBackTH = 3;                    // hidden accumulators in TMEM and GELU tiles in shared memory:
+constexpr int kBackSlots = 4;                 // weight ring slots of kW1c == kW2c bytes: every MLP chunk consumes two
+                                              // (W2_j, W1_j+3), so four slots keep the TMA stream two chunks ahead
+constexpr int kBackHB = 2;                    // GELU tiles in shared memory: one per epilogue warp group (chunk parity)
+constexpr int kBackTH = 3;                    // hidden accumulators in TMEM:
                                               // W1 chunk c+3 is issued when GELU(c) is done
 constexpr int kBackLoads = 2 * kNChunk;       // weight chunk loads per tile
 constexpr int kCQ = kKP / 4;                  // 36 accumulator columns per epilogue thread
@@ -57,8 +61,8 @@ struct BackBars {
   uint64_t lnfull;       // epilogue -> control: LN2(u) tile staged (16 warp arrivals)
   uint64_t pfull;        // proj accumulator ready
   uint64_t thfull[kBackTH];   // hidden accumulator t_h[s] ready
-  uint64_t hbfull[kBackTH];   // epilogue -> control: GELU tile hbuf[s] staged (8 warp arrivals: the chunk's group)
-  uint64_t hbfree[kBackTH];   // W2 chunk MMA done: hbuf[s] reusable
+  uint64_t hbfull[kBackHB];   // epilogue -> control: GELU tile hbuf[s] staged (8 warp arrivals: the chunk's group)
+  uint64_t hbfree[kBackHB];   // W2 chunk MMA done: hbuf[s] reusable
   uint64_t yfull;             // a tile's last W2 chunk MMA done: y accumulator complete (one phase per tile)
   uint64_t wfull[kBackSlots];    // TMA arrival of a ring slot
   uint64_t wempty[kBackSlots];   // the MMAs reading a ring slot are done
@@ -130,8 +134,8 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__rest
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *abuf = smem;                      // 2 x { out2 tile (token-contiguous), then LN2(u) (channel-contiguous) }
   uint8_t *wpb = abuf + 2 * kTile144;        // Wp, resident
-  uint8_t *hbuf = wpb + kW144;               // 3 x GELU(hidden chunk)
-  uint8_t *ring = hbuf + kBackTH * kHTile;   // 3 weight chunk slots
+  uint8_t *hbuf = wpb + kW144;               // kBackHB x GELU(hidden chunk)
+  uint8_t *ring = hbuf + kBackHB * kHTile;   // kBackSlots weight chunk slots
   BackVec *V = reinterpret_cast<BackVec *>(ring + kBackSlots * kW1c);
   __shared__ BackBars bars;
   __shared__ uint32_t tmem_slot;
@@ -151,8 +155,9 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__rest
     mbar_init(&bars.wpfull, 1);
     mbar_init(&bars.yfull, 1);
 #pragma unroll
-    for (int i = 0; i < kBackTH; ++i) {
-      mbar_init(&bars.thfull[i], 1);
+    for (int i = 0; i < kBackTH; ++i) mbar_init(&bars.thfull[i], 1);
+#pragma unroll
+    for (int i = 0; i < kBackHB; ++i) {
       mbar_init(&bars.hbfull[i], kBackEpi / 64);
       mbar_init(&bars.hbfree[i], 1);
     }
@@ -250,18 +255,18 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__rest
 #pragma unroll 1
       for (int j = 0; j < kNChunk; ++j) {
         const int c = c0 + j;
-        mbar_wait(&bars.hbfull[c % kBackTH], (c / kBackTH) & 1);
+        mbar_wait(&bars.hbfull[c % kBackHB], (c / kBackHB) & 1);
         tr(10 + j);
         tc_fence_after();
         const uint32_t w2 = next_chunk();
         tr(30 + j);
-        const uint32_t hh = hb + (c % kBackTH) * kHTile;
+        const uint32_t hh = hb + (c % kBackHB) * kHTile;
 #pragma unroll
         for (int s = 0; s < kNH / 16; ++s)
           umma_elect(t_y, make_desc(hh + s * 2 * kCS, kCS, kRSH), make_desc(w2 + s * 2 * kCS, kCS, kRSH), idesc144,
                      (j > 0 || s > 0));
         release_chunk();
-        commit_elect(&bars.hbfree[c % kBackTH]);
+        commit_elect(&bars.hbfree[c % kBackHB]);
         if (j == kNChunk - 1) commit_elect(&bars.yfull);
         if (j + 3 < kNChunk) mma1(c + 3);   // t_h[c%3] was drained by GELU(chunk c) before hbfull[c%3]
         if (j == kNChunk - 2 && it + 1 < ntile) proj(it + 1);   // its out2 tile is published at chunk 6;
@@ -462,13 +467,14 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__rest
         if ((c & 1) == (quarter & 1)) {
           const uint32_t par = (c / kBackTH) & 1;
           mbar_wait(&bars.thfull[c % kBackTH], par);
-          if (c >= kBackTH) mbar_wait(&bars.hbfree[c % kBackTH], par ^ 1);   // W2 chunk c-3 has consumed hbuf[c%3]
+          if (c >= kBackHB)   // W2 chunk c-2 (this group's previous chunk) has consumed hbuf[c%2]
+            mbar_wait(&bars.hbfree[c % kBackHB], ((c / kBackHB) & 1) ^ 1);
           tc_fence_after();
           tr(10 + j);
           const int hcol = (quarter >> 1) * 2 * kHQ;   // 32 hidden columns of this thread
           float hv[2 * kHQ];
           tmem_ld32(tcol(t_h + (c % kBackTH) * kNH, q4, hcol), hv);
-          uint8_t *dst = hbuf + (c % kBackTH) * kHTile + cm_offset(tok, hcol, kRSH, kCS);
+          uint8_t *dst = hbuf + (c % kBackHB) * kHTile + cm_offset(tok, hcol, kRSH, kCS);
 #pragma unroll
           for (int gg = 0; gg < 4; ++gg) {
             const float *v = hv + gg * 8;
@@ -482,7 +488,7 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__rest
           fence_async_smem();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bars.hbfull[c % kBackTH]);
+          if (lane == 0) mbar_arrive(&bars.hbfull[c % kBackHB]);
         }
         tr(30 + j);
         if (has_next) {

@@ -22,6 +22,12 @@ for prec in ("fp16", "fp32"):
         r = heatmap.final_preds_cuda(out)
         torch.cuda.synchronize()
         print(prec, frames, float(out.abs().max()), int(r["idx"].sum()))
+    # a0 + a1 fused hand-off kernel on a bf16 channels-last feature map (ragged tile: 24 * 16 = 384 = 1.5 CTA tiles)
+    feats = torch.randn(5 * b, 48, h, w).to(torch.bfloat16).cuda().contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(17, 48, 1, 1) / 7).cuda()
+    out = model.forward_from_features(feats, syn.synth_margin(b).cuda(), wt, torch.zeros(17).cuda())[0]
+    torch.cuda.synchronize()
+    print(prec, "from features", float(out.abs().max()))
 m = ModulatedDeformConv(17, 17, 3, padding=3, dilation=3, deformable_groups=17).cuda()
 x = torch.randn(2, 17, h, w, device="cuda", requires_grad=True)
 off = (torch.randn(2, 306, h, w, device="cuda") * 2).requires_grad_(True)
