@@ -198,21 +198,29 @@ __device__ __forceinline__ uint32_t tcol(uint32_t base, int q4, int col) {
 }
 
 // ------------------------------------------------------------------ tc_apply
+// One CTA per (clip, run of `tiles_per_cta` consecutive tiles), two resident per SM: W_eff, the TMEM
+// accumulator and the barrier are set up once per CTA; the next tile's vn image streams in with cp.async
+// while the current tile's epilogue runs (the operand buffer is dead as soon as the UMMAs have completed).
+constexpr uint32_t kApplyStage = 2 * kTM * kHS * 2;   // [2 heads][128 tokens][68] 16-bit output tile
 template <bool F16>
 __global__ void __launch_bounds__(kApplyThreads, 2)
 tc_apply_kernel(const uint8_t *__restrict__ vn_img, const uint8_t *__restrict__ weff_img,
-                const float *__restrict__ beff, unsigned short *__restrict__ obuf, int Tout, int tiles) {
+                const float *__restrict__ beff, unsigned short *__restrict__ obuf, int Tout, int tiles,
+                int tiles_per_cta) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *a = smem;
   uint8_t *w = smem + kTile144;
+  unsigned short *stage = reinterpret_cast<unsigned short *>(w + kW144);
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
   __shared__ float sb[kKP];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q4 = warp & 3, half = warp >> 2;
   const int tok = q4 * 32 + lane;
-  const int b = blockIdx.y, tile = blockIdx.x;
-  const int t0 = tile * kTM, nvalid = min(kTM, Tout - t0);
-  cp_async_block(a, vn_img + ((size_t)b * tiles + tile) * kTile144, kTile144, kApplyThreads);
+  const int b = blockIdx.y;
+  const int tile_begin = blockIdx.x * tiles_per_cta, tile_end = min(tiles, tile_begin + tiles_per_cta);
+  if (tile_begin >= tile_end) return;
+  const uint8_t *vb = vn_img + (size_t)b * tiles * kTile144;
+  cp_async_block(a, vb + (size_t)tile_begin * kTile144, kTile144, kApplyThreads);
   cp_async_block(w, weff_img + (size_t)b * kW144, kW144, kApplyThreads);
   cp_async_commit();
   for (int n = threadIdx.x; n < kKP; n += kApplyThreads) sb[n] = beff[(size_t)b * kKP + n];
@@ -221,63 +229,72 @@ tc_apply_kernel(const uint8_t *__restrict__ vn_img, const uint8_t *__restrict__ 
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, 256);
-  cp_async_wait<0>();
-  fence_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tm = tmem_slot;
-  if (threadIdx.x == 0) {
-    const uint32_t idesc = make_idesc_16(kKP, false, false, F16 ? 0u : 1u);
-    const uint32_t aa = smem_u32(a), ww = smem_u32(w);
-#pragma unroll
-    for (int s = 0; s < kKP / 16; ++s)
-      umma_bf16(tm, make_desc(aa + s * 2 * kCS, kCS, kRS144), make_desc(ww + s * 2 * kCS, kCS, kRS144), idesc, s > 0);
-    umma_commit(&bar);
-  }
-  mbar_wait(&bar, 0);
-  tc_fence_after();
-  // token-major store obuf[b][head][token][68] (16 bit) == the reference's scramble buffer.  A tile's
-  // rows of one head are ONE contiguous block of nvalid * 136 bytes in global memory: the tile is
-  // assembled in shared memory (over the dead operand tile) and leaves with two bulk (TMA) stores
-  // instead of 18 scattered 8-byte stores per thread (each warp store touched 32 separate sectors).
   unsigned short *ob = obuf + (size_t)b * kC * Tout;
-  const bool bulk = ((Tout | nvalid) & 1) == 0;   // 16-byte size / alignment of the blocks
-  unsigned short *stage = reinterpret_cast<unsigned short *>(a);   // [2 heads][128 tokens][68]
-#pragma unroll 1
-  for (int g = 0; g < 9; ++g) {
-    const int col = half * 72 + g * 8;
-    float v[8];
-    tmem_ld8(tcol(tm, q4, col), v);
-    if (tok < nvalid) {
+  uint32_t tm = 0, phase = 0;
+  for (int tile = tile_begin; tile < tile_end; ++tile) {
+    const int t0 = tile * kTM, nvalid = min(kTM, Tout - t0);
+    cp_async_wait<0>();        // this tile's operand image (and W_eff on the first tile)
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();           // also: the previous tile's output tile has left `stage` (thread 0 waited)
+    tc_fence_after();
+    tm = tmem_slot;
+    if (threadIdx.x == 0) {
+      const uint32_t idesc = make_idesc_16(kKP, false, false, F16 ? 0u : 1u);
+      const uint32_t aa = smem_u32(a), ww = smem_u32(w);
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int n4 = col + 4 * q;
-        if (n4 < kC) {
-          const int h = n4 >= kHS ? 1 : 0, cp = n4 - h * kHS;
-          uint2 pk;
-          pk.x = pack16x2<F16>(v[4 * q] + sb[n4], v[4 * q + 1] + sb[n4 + 1]);
-          pk.y = pack16x2<F16>(v[4 * q + 2] + sb[n4 + 2], v[4 * q + 3] + sb[n4 + 3]);
-          if (bulk)
-            *reinterpret_cast<uint2 *>(stage + (h * kTM + tok) * kHS + cp) = pk;
-          else
-            *reinterpret_cast<uint2 *>(ob + ((size_t)h * Tout + t0 + tok) * kHS + cp) = pk;
+      for (int s = 0; s < kKP / 16; ++s)
+        umma_bf16(tm, make_desc(aa + s * 2 * kCS, kCS, kRS144), make_desc(ww + s * 2 * kCS, kCS, kRS144), idesc, s > 0);
+      umma_commit(&bar);
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    if (tile + 1 < tile_end) {   // the UMMAs have read `a`: the next tile's image streams in under the epilogue
+      cp_async_block(a, vb + (size_t)(tile + 1) * kTile144, kTile144, kApplyThreads);
+      cp_async_commit();
+    }
+    // token-major store obuf[b][head][token][68] (16 bit) == the reference's scramble buffer.  A tile's
+    // rows of one head are ONE contiguous block of nvalid * 136 bytes in global memory: the tile is
+    // assembled in shared memory and leaves with two bulk (TMA) stores instead of 18 scattered 8-byte
+    // stores per thread (each warp store touched 32 separate sectors).
+    const bool bulk = ((Tout | nvalid) & 1) == 0;   // 16-byte size / alignment of the blocks
+#pragma unroll 1
+    for (int g = 0; g < 9; ++g) {
+      const int col = half * 72 + g * 8;
+      float v[8];
+      tmem_ld8(tcol(tm, q4, col), v);
+      if (tok < nvalid) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int n4 = col + 4 * q;
+          if (n4 < kC) {
+            const int h = n4 >= kHS ? 1 : 0, cp = n4 - h * kHS;
+            uint2 pk;
+            pk.x = pack16x2<F16>(v[4 * q] + sb[n4], v[4 * q + 1] + sb[n4 + 1]);
+            pk.y = pack16x2<F16>(v[4 * q + 2] + sb[n4 + 2], v[4 * q + 3] + sb[n4 + 3]);
+            if (bulk)
+              *reinterpret_cast<uint2 *>(stage + (h * kTM + tok) * kHS + cp) = pk;
+            else
+              *reinterpret_cast<uint2 *>(ob + ((size_t)h * Tout + t0 + tok) * kHS + cp) = pk;
+          }
         }
       }
     }
-  }
-  if (bulk) {
-    fence_async_smem();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const uint32_t bytes = (uint32_t)nvalid * kHS * 2;
+    tc_fence_before();         // the accumulator is rewritten by the next tile's UMMAs
+    if (bulk) {
+      fence_async_smem();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const uint32_t bytes = (uint32_t)nvalid * kHS * 2;
 #pragma unroll
-      for (int h = 0; h < 2; ++h)
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(ob + ((size_t)h * Tout + t0) * kHS),
-                     "r"(smem_u32(stage + h * kTM * kHS)), "r"(bytes)
-                     : "memory");
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the shared tile has been read
+        for (int h = 0; h < 2; ++h)
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(ob + ((size_t)h * Tout + t0) * kHS),
+                       "r"(smem_u32(stage + h * kTM * kHS)), "r"(bytes)
+                       : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the shared tile has been read
+      }
     }
   }
   tc_fence_before();
@@ -344,7 +361,8 @@ void pack_image(bool f16, const float *src, int ld, int row0, int col0, int rv, 
     pack_image_kernel<false><<<ceil_div(rp * cp, 256), 256, 0, st>>>(src, ld, row0, col0, rv, cv, colscale, dst, rp, cp);
 }
 
-constexpr size_t kApplySmem = (size_t)kTile144 + kW144;
+constexpr size_t kApplySmem = (size_t)kTile144 + kW144 + kApplyStage;
+static_assert(2 * (kApplySmem + 2048) <= 228 * 1024, "two tc_apply CTAs per SM");
 constexpr size_t kBackSmem = (size_t)2 * kTile144 + kW144 + kBackHB * kHTile + kBackSlots * kW1c + sizeof(BackVec);
 static_assert(kBackSmem + 1024 <= 227 * 1024, "tc_back shared memory");
 
@@ -393,7 +411,11 @@ int forward_tc_t(const void *packed_fp32, const void *packed_tc, const float *x,
   }
   {
     LaunchScope ls(K_TC_APPLY, st);
-    tc_apply_kernel<F16><<<dim3(W.tiles, b), kApplyThreads, kApplySmem, st>>>(vn, weff, beff, obuf, W.tout, W.tiles);
+    // runs of consecutive tiles per CTA: ~2 CTAs per SM over the whole batch, at least one tile each
+    const int want = max(1, ceil_div(2 * num_sms(), b));
+    const int tpc = max(1, ceil_div(W.tiles, min(W.tiles, want)));
+    tc_apply_kernel<F16><<<dim3(ceil_div(W.tiles, tpc), b), kApplyThreads, kApplySmem, st>>>(vn, weff, beff, obuf, W.tout,
+                                                                                            W.tiles, tpc);
   }
   {
     LaunchScope ls(K_TC_BACK, st);
