@@ -15,7 +15,7 @@ namespace otp {
 using namespace tc;
 namespace {
 
-constexpr int kPyThreads = 512;
+constexpr int kPyThreads = 1024;
 constexpr int kPyTM = 128;
 constexpr int kPyN = 32;   // UMMA N (17 outputs padded)
 
