@@ -56,6 +56,12 @@ def test_shape_queries_and_unsupported_widths():
     # empty batches are a no-op, not an error (reference handles B=0 tensors)
     assert lib.otp_final_preds(None, 0, 17, 8, 8, None, None, None, None, None, None, None) == 0
     assert lib.otp_fusion_sum(None, 0, 17, 64, None, None, None) == 0
+    # a0 + a1 hand-off kernel: widths it is not built for are refused (status 2), bad frame windows are
+    # argument errors, an empty batch is a no-op
+    assert lib.otp_final_layer_fusion_sum(None, 1, 1, None, None, 5, 2, 44, 17, 64, None, None, None, None) == 2
+    assert lib.otp_final_layer_fusion_sum(None, 1, 1, None, None, 5, 2, 48, 16, 64, None, None, None, None) == 2
+    assert lib.otp_final_layer_fusion_sum(None, 1, 1, None, None, 4, 2, 48, 17, 64, None, None, None, None) == 1
+    assert lib.otp_final_layer_fusion_sum(None, 1, 1, None, None, 5, 0, 48, 17, 64, None, None, None, None) == 0
 
 
 def manifest():
@@ -102,6 +108,10 @@ def test_cpu_tensors_are_rejected_like_the_reference():
         blk(torch.zeros(1, 17, 8, 8))
     with pytest.raises(NotImplementedError):   # training-mode semantics are not built
         ConvTransformer(17, 17, 1, 3, 64, arch=(0, 1, 0), h=8).train()(torch.zeros(1, 17, 8, 8))
+    head = OTPose(default_cfg((8, 8))).eval()
+    with pytest.raises(NotImplementedError):   # the feature hand-off boundary keeps the same contract
+        head.forward_from_features(torch.zeros(5, 48, 8, 8), torch.zeros(1, 4, dtype=torch.int64),
+                                   torch.zeros(17, 48, 1, 1), torch.zeros(17))
 
 
 def test_synthetic_is_deterministic_and_nontrivial():
