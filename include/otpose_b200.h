@@ -225,6 +225,19 @@ int otp_conv2d(const float *x, long long x_bstride, const float *x_add, long lon
                long long residual_bstride, float *y, long long y_bstride, int b, int cin, int h,
                int w, int cout, int k, int dilation, int relu, otp_stream_t stream);
 
+/* a12 (training config): backward of otp_conv2d for the weights and the bias -- what autograd runs through
+ * ATen's convolution backward in the reference for the offset / mask convs of model/OTPose.py:168-177 when
+ * ModulatedDeformConvFunction.backward (functions/deform_conv.py:148-167) hands their gradients back.
+ *   grad_weight (cout, cin, k, k) = sum_{b,h,w} grad_out[b,o,h,w] * x[b,c,h+(i-k/2)d, w+(j-k/2)d]
+ *   grad_bias   (cout) or NULL    = sum_{b,h,w} grad_out[b,o,h,w]
+ * x / grad_out are channel slices (ptr, batch stride in elements) like otp_conv2d; accumulate != 0 adds to
+ * the existing gradients.  Deterministic (fixed-order reduction of per-slice partials in `workspace`).
+ * grad_input needs no entry point: it is otp_conv2d(grad_out) with the weights transposed and flipped. */
+size_t otp_conv2d_wgrad_workspace_bytes(int b, int cin, int h, int w, int cout, int k);
+int otp_conv2d_wgrad(const float *x, long long x_bstride, const float *grad_out, long long go_bstride,
+                     float *grad_weight, float *grad_bias, int b, int cin, int h, int w, int cout, int k,
+                     int dilation, int accumulate, void *workspace, size_t workspace_bytes, otp_stream_t stream);
+
 /* a7, 16-bit tensor-core variant of otp_conv2d (dilation 1, w % 8 == 0, <= 96 channels):
  * implicit GEMM on tcgen05 over three pre-shifted 16-bit copies of the input rows (no im2col
  * tile), fp32 accumulate / bias / residual / output.  `packed` = otp_conv2d_tc_pack of the

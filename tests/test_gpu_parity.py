@@ -656,3 +656,63 @@ def test_head_from_channels_last_bf16_features():
                                          wt.cuda(), bias.cuda())
     for n, o, e in zip(NAMES, outs_g, outs):
         assert torch.equal(o, e), n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("b,cin,cout,h,w,k,d,bias", [(3, 32, 45, 12, 20, 3, 3, False), (2, 5, 7, 9, 11, 1, 1, True),
+                                                      (2, 20, 20, 10, 72, 3, 1, True), (1, 33, 70, 7, 130, 3, 6, False)])
+def test_conv2d_backward_vs_float64_autograd(b, cin, cout, h, w, k, d, bias):
+    """a12: native backward of the small-channel conv (the offset / mask convs of model/OTPose.py:168-177):
+    grad_input (otp_conv2d with transposed, flipped weights), grad_weight / grad_bias (otp_conv2d_wgrad) against
+    ATen's float64 autograd of the same F.conv2d; bit-reproducible."""
+    import torch.nn.functional as F
+    from otpose_b200.model.conv2d_fn import conv2d
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(b, cin, h, w, generator=g).cuda().requires_grad_(True)
+    wt = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).cuda().requires_grad_(True)
+    bs = torch.randn(cout, generator=g).cuda().requires_grad_(True) if bias else None
+    go = torch.randn(b, cout, h, w, generator=g).cuda()
+    y = conv2d(x, wt, bs, d)
+    grads = torch.autograd.grad(y, [x, wt] + ([bs] if bias else []), go)
+    x64, w64 = x.detach().double().requires_grad_(True), wt.detach().double().requires_grad_(True)
+    b64 = bs.detach().double().requires_grad_(True) if bias else None
+    y64 = F.conv2d(x64, w64, b64, stride=1, padding=d * (k // 2), dilation=d)
+    ref = torch.autograd.grad(y64, [x64, w64] + ([b64] if bias else []), go.double())
+    assert rel(y, y64.float()) < 1e-5
+    for name, a, r in zip(("grad_input", "grad_weight", "grad_bias"), grads, ref):
+        assert rel(a, r.float()) < 2e-5, name
+    again = torch.autograd.grad(conv2d(x, wt, bs, d), [x, wt] + ([bs] if bias else []), go)
+    for a, c in zip(grads, again):
+        assert torch.equal(a, c)
+
+
+@pytest.mark.gpu
+def test_offset_mask_conv_dcn_stage_trains_natively():
+    """a8 + a9 backward as one unit: offsets = conv(trans), masks = conv(trans), out = DCN(x, offsets, masks)
+    (model/OTPose.py:382-384) through the library's conv and DCN autograd functions, gradients of every leaf
+    against the float64 autograd of F.conv2d + torchvision.ops.deform_conv2d."""
+    import torch.nn.functional as F
+    import torchvision
+    from otpose_b200.model.conv2d_fn import conv2d
+    b, j, cdef, h, w, d = 2, 17, 32, 12, 10, 3
+    g = torch.Generator().manual_seed(5)
+    trans = torch.randn(b, cdef, h, w, generator=g).cuda().requires_grad_(True)
+    x = torch.randn(b, j, h, w, generator=g).cuda().requires_grad_(True)
+    w_off = (torch.randn(18 * j, cdef, 3, 3, generator=g) * 0.05).cuda().requires_grad_(True)
+    w_msk = (torch.randn(9 * j, cdef, 3, 3, generator=g) * 0.05).cuda().requires_grad_(True)
+    dcn = ModulatedDeformConv(j, j, 3, padding=d, dilation=d, deformable_groups=j).cuda()
+    with torch.no_grad():
+        dcn.weight.copy_(torch.randn(dcn.weight.shape, generator=g) * 0.1)
+        dcn.bias.copy_(torch.randn(j, generator=g) * 0.1)
+    out = dcn(x, conv2d(trans, w_off, None, d), conv2d(trans, w_msk, None, d))
+    go = torch.randn(out.shape, generator=g).cuda()
+    leaves = [trans, x, w_off, w_msk, dcn.weight, dcn.bias]
+    grads = torch.autograd.grad(out, leaves, go)
+    l64 = [t.detach().double().requires_grad_(True) for t in leaves]
+    off64 = F.conv2d(l64[0], l64[2], None, 1, d, d)
+    msk64 = F.conv2d(l64[0], l64[3], None, 1, d, d)
+    out64 = torchvision.ops.deform_conv2d(l64[1], off64, l64[4], l64[5], stride=1, padding=d, dilation=d, mask=msk64)
+    ref = torch.autograd.grad(out64, l64, go.double())
+    assert rel(out, out64.float()) < 1e-4
+    for name, a, r in zip(("trans", "x", "w_offset", "w_mask", "dcn.weight", "dcn.bias"), grads, ref):
+        assert rel(a, r.float()) < 1e-4, name
