@@ -9,7 +9,7 @@
 //   grad_bias[o] = sum_{b,h,w} grad_output[b,o,h,w]                                              (this file)
 //
 // grad_weight is an implicit GEMM dY (Cout x N) . im2col(x) (N x Cin k^2) with N = B*H*W (221 k at 32 clips):
-// a CTA owns a 32 x 32 (o, c) tile of ONE tap over a slice of the image rows, stages 32 x 64 fp32 tiles of
+// a CTA owns a 32 x 32 (o, c) tile of ONE tap over a slice of the image rows, stages 32 x W fp32 tiles of
 // dY and of the shifted x row in shared memory and accumulates 2 x 2 outputs per thread from 16-byte reads;
 // the per-slice partials are summed in fixed order by a second kernel, so the result is bit-reproducible
 // (the reference's cuDNN algorithms are not guaranteed to be).  fp32 CUDA cores: first correct version of
@@ -19,7 +19,7 @@
 namespace otp {
 namespace {
 constexpr int kWgT = 32;          // tile edge in output / input channels
-constexpr int kWgPx = 64;         // pixels per staged chunk
+constexpr int kWgPx = 128;        // pixels per staged chunk (a whole image row for W <= 128)
 constexpr int kWgThreads = 256;   // 16 x 16 threads, 2 x 2 outputs each
 
 __global__ void __launch_bounds__(kWgThreads)
@@ -40,15 +40,16 @@ conv_wgrad_kernel(const float *__restrict__ x, long long x_bs, const float *__re
     const float *dyr = dy + (size_t)b * dy_bs + (size_t)h * W;
     const float *xr = x + (size_t)b * x_bs + (size_t)hh * W;
     for (int w0 = 0; w0 < W; w0 += kWgPx) {
+      const int npx = (min(kWgPx, W - w0) + 3) & ~3;   // staged / contracted pixels of this chunk (zero padded to 4)
       __syncthreads();
-      for (int e = threadIdx.x; e < kWgT * kWgPx; e += kWgThreads) {
-        const int r = e / kWgPx, px = e % kWgPx, w = w0 + px, ww = w + dj;
+      for (int e = threadIdx.x; e < kWgT * npx; e += kWgThreads) {
+        const int r = e / npx, px = e % npx, w = w0 + px, ww = w + dj;
         ds[r][px] = (o0 + r < Cout && w < W) ? __ldg(dyr + (size_t)(o0 + r) * P + w) : 0.f;
         xs[r][px] = (c0 + r < Cin && w < W && ww >= 0 && ww < W) ? __ldg(xr + (size_t)(c0 + r) * P + ww) : 0.f;
       }
       __syncthreads();
 #pragma unroll 4
-      for (int px = 0; px < kWgPx; px += 4) {
+      for (int px = 0; px < npx; px += 4) {
         const float4 d0 = *reinterpret_cast<const float4 *>(&ds[2 * to][px]);
         const float4 d1 = *reinterpret_cast<const float4 *>(&ds[2 * to + 1][px]);
         const float4 x0 = *reinterpret_cast<const float4 *>(&xs[2 * tc][px]);

@@ -16,16 +16,28 @@ from .. import _lib
 __all__ = ["Conv2dFunction", "conv2d"]
 
 
+_CIN_CHUNK = 48   # otp_conv2d keeps the (Cin*k*k, 16) weight tile of a CTA in shared memory: built for small Cin
+
+
 def _launch_conv(x, weight, bias, dilation):
+    """y = conv(x) + bias.  Wide inputs (the grad_input conv of a 32 -> 306 layer has Cin = 306) are run as a
+    chain over input-channel chunks, each launch adding the previous partial through the kernel's fused
+    residual input (same thread reads and writes an element, so the chain runs in place)."""
     lib = _lib.load()
     b, cin, h, w = x.shape
     cout, k = weight.shape[0], weight.shape[2]
     y = torch.empty((b, cout, h, w), dtype=torch.float32, device=x.device)
     if b:
+        p = h * w
         with torch.cuda.device(x.device):
-            _lib.check(lib.otp_conv2d(_lib.dptr(x), cin * h * w, None, 0, _lib.dptr(weight),
-                                      _lib.dptr(bias, allow_none=True), None, 0, y.data_ptr(), cout * h * w, b, cin,
-                                      h, w, cout, k, dilation, 0, _lib.stream_ptr(x.device)), "otp_conv2d")
+            st = _lib.stream_ptr(x.device)
+            for c0 in range(0, cin, _CIN_CHUNK):
+                c1 = min(cin, c0 + _CIN_CHUNK)
+                wc = weight if (c0 == 0 and c1 == cin) else weight[:, c0:c1].contiguous()
+                _lib.check(lib.otp_conv2d(x.data_ptr() + 4 * c0 * p, cin * p, None, 0, _lib.dptr(wc),
+                                          _lib.dptr(bias, allow_none=True) if c0 == 0 else None,
+                                          y.data_ptr() if c0 else None, cout * p, y.data_ptr(), cout * p, b, c1 - c0,
+                                          h, w, cout, k, dilation, 0, st), "otp_conv2d")
     return y
 
 

@@ -16,6 +16,8 @@ x = torch.randn(b, cin, h, w, device="cuda", requires_grad=True)
 wt = (torch.randn(cout, cin, 3, 3, device="cuda") * 0.05).requires_grad_(True)
 go = torch.randn(b, cout, h, w, device="cuda")
 for what, leaves in (("grad_input", [x]), ("grad_weight", [wt]), ("both", [x, wt])):
+    x.requires_grad_(any(x is t for t in leaves))          # the Function computes the gradients its inputs ask for
+    wt.requires_grad_(any(wt is t for t in leaves))
     y = conv2d(x, wt, None, d)
     for _ in range(2):
         torch.autograd.grad(y, leaves, go, retain_graph=True)
