@@ -136,16 +136,18 @@ def main():
         save(name, x=x, seed=2024, n_head=nh, arch=np.array(arch), **{f"out{i}": o for i, o in enumerate(outs)})
 
     # ---- RSB chains ---------------------------------------------------------
-    for name, cin, cout, seed in (("rsb_def_fuse", 17, 17, 21), ("rsb_combine", 51, 32, 22)):
+    for name, cin, cout, seed, hw in (("rsb_def_fuse", 17, 17, 21, (9, 7)), ("rsb_combine", 51, 32, 22, (9, 7)),
+                                      ("rsb_combine_w8", 51, 32, 23, (10, 8))):
         m = CHAIN_RSB_BLOCKS(cin, cout, 2).eval()
         sh = shapes_of(m)
         manifest[name] = {k: list(v) for k, v in sh.items()}
         m.load_state_dict(syn.fill_state_dict(sh, seed=2024))
-        x = torch.from_numpy(np.random.default_rng(seed).standard_normal((2, cin, 9, 7)).astype(np.float32))
+        x = torch.from_numpy(np.random.default_rng(seed).standard_normal((2, cin) + hw).astype(np.float32))
         save(name, x=x, seed=2024, out=m(x))
 
     # ---- the reference OTPose.forward itself (backbone stubbed) -------------
-    for name, b, h, w in (("head_16x12", 2, 16, 12), ("head_24x20", 1, 24, 20)):
+    # head_16x16: W % 8 == 0, so the 16-bit modes reach the tcgen05 RSB convs (conv_tc) on a golden fixture
+    for name, b, h, w in (("head_16x12", 2, 16, 12), ("head_24x20", 1, 24, 20), ("head_16x16", 1, 16, 16)):
         model = ref_otpose.OTPose(make_cfg(h, w), phase="validate").eval()
         sh = shapes_of(model)
         if "head" not in manifest:

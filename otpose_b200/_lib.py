@@ -154,20 +154,37 @@ def profile_read():
 
 
 class _WorkspacePool:
-    """One growing scratch buffer per (device, stream, tag); kernels are stream-ordered so
-    consecutive calls on the same stream can share it, and branches running concurrently on
-    different streams (the two temporal encoders) never do."""
+    """Scratch buffers for the kernels' workspaces.
+
+    Eager calls: one growing buffer per (device, stream, tag); kernels are stream-ordered, so consecutive
+    calls on the same stream share it and branches running concurrently on different streams (the two
+    temporal encoders) never do.  A regrown buffer's predecessor goes back to the caching allocator, which
+    re-issues it only to later work on the same stream.
+
+    During CUDA-graph capture the pool is bypassed: the buffer is a plain ``torch.empty`` made inside the
+    capture, i.e. it lives in the capturing graph's private memory pool for as long as that graph exists.
+    A captured graph therefore never holds a pointer into a pooled buffer that a later, larger eager call
+    (or the capture of another shape) could regrow and free.
+    """
 
     def __init__(self):
         self._bufs = {}
 
     def get(self, nbytes: int, device, tag: str = "ws") -> torch.Tensor:
+        if torch.cuda.is_current_stream_capturing():
+            return torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
         key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream, tag)
         buf = self._bufs.get(key)
         if buf is None or buf.numel() < nbytes:
             buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
             self._bufs[key] = buf
         return buf
+
+    def drop_stream(self, device, stream) -> None:
+        """Forget the buffers keyed by a stream that is going away (a graph warm-up stream)."""
+        dev, ptr = torch.device(device).index, stream.cuda_stream
+        for key in [k for k in self._bufs if k[0] == dev and k[1] == ptr]:
+            del self._bufs[key]
 
     def clear(self):
         self._bufs.clear()

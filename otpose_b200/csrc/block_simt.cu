@@ -461,12 +461,12 @@ static int block_forward_simt_t(const void *packed, const float *x, float *y, in
   const size_t smem_front = (size_t)C * (kLDX + 3 * kLD) * 4 + red_bytes;
   const size_t smem_apply = (size_t)C * (kLDX + kLD) * 4 + red_bytes;
   const size_t smem_back = (size_t)C * 3 * kLD * 4 + red_bytes;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(block_front_kernel<C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_front);
-    cudaFuncSetAttribute(block_apply_kernel<C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_apply);
-    cudaFuncSetAttribute(block_back_kernel<C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_back);
-    attr_done = true;
+  static PerDeviceOnce attr;
+  if (attr.first()) {
+    if (!set_max_smem(block_front_kernel<C_>, smem_front, "block_front_kernel") ||
+        !set_max_smem(block_apply_kernel<C_>, smem_apply, "block_apply_kernel") ||
+        !set_max_smem(block_back_kernel<C_>, smem_back, "block_back_kernel"))
+      return OTP_ERR_CUDA;
   }
   const float qscale = 1.0f / sqrtf((float)Cfg::HS);
   {

@@ -384,14 +384,14 @@ int forward_tc_t(const void *packed_fp32, const void *packed_tc, const float *x,
   uint8_t *weff = ws + W.weff;
   uint8_t *vn = ws + W.vn;
   unsigned short *obuf = reinterpret_cast<unsigned short *>(ws + W.obuf);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(tc_front1_kernel<F16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFront1Smem);
-    cudaFuncSetAttribute(tc_front1_kernel<F16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFront1Smem);
-    cudaFuncSetAttribute(tc_apply_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kApplySmem);
-    cudaFuncSetAttribute(tc_back_kernel<F16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBackSmem);
-    cudaFuncSetAttribute(tc_back_kernel<F16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBackSmem);
-    attr_done = true;
+  static PerDeviceOnce attr;
+  if (attr.first()) {
+    if (!set_max_smem(tc_front1_kernel<F16, false>, kFront1Smem, "tc_front1_kernel") ||
+        !set_max_smem(tc_front1_kernel<F16, true>, kFront1Smem, "tc_front1_kernel") ||
+        !set_max_smem(tc_apply_kernel<F16>, kApplySmem, "tc_apply_kernel") ||
+        !set_max_smem(tc_back_kernel<F16, false>, kBackSmem, "tc_back_kernel") ||
+        !set_max_smem(tc_back_kernel<F16, true>, kBackSmem, "tc_back_kernel"))
+      return OTP_ERR_CUDA;
   }
   {
     LaunchScope ls(K_TC_FRONT, st);

@@ -29,15 +29,44 @@ inline int check_launch(const char *kernel) {
     if (!(cond)) return ::otp::fail_arg(#cond); \
   } while (0)
 
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  return dev % kMaxDevices;
+}
+
+// per-device cache: a process may drive several GPUs (DataParallel, model.to("cuda:1"))
 inline int num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-      sms = 148;  // B200
+  static int sms[kMaxDevices] = {};
+  const int dev = current_device();
+  if (sms[dev] == 0) {
+    if (cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms[dev] <= 0)
+      sms[dev] = 148;  // B200
   }
-  return sms;
+  return sms[dev];
+}
+
+// cudaFuncSetAttribute applies to the CURRENT device only: one flag per device ordinal, not per process.
+struct PerDeviceOnce {
+  bool done[kMaxDevices] = {};
+  bool first() {
+    const int d = current_device();
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
+// opt a kernel in to `bytes` of dynamic shared memory on the current device; false (+ otp_last_error) on failure
+template <class F>
+inline bool set_max_smem(F *kernel, size_t bytes, const char *name) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) {
+    set_error("%s: cudaFuncSetAttribute(%zu B dynamic shared memory): %s", name, bytes, cudaGetErrorString(e));
+    return false;
+  }
+  return true;
 }
 
 // Kernel ids for launch counting and the optional per-kernel event timing

@@ -269,10 +269,11 @@ static bool launch_strip(const float *x, long long x_bs, const float *xa, long l
   const int th = 8;   // strip height (2x2 pixel blocks per thread; the halo costs 10/8)
   const size_t smem = ((size_t)((cin * (th + 2) * (w + 2) + 3) & ~3) + (size_t)cin * 9 * CO) * sizeof(float);
   if (smem > 160 * 1024) return false;
-  static size_t attr = 0;
-  if (smem > attr) {
-    cudaFuncSetAttribute(conv3x3_strip_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = smem;
+  static size_t attr[kMaxDevices] = {};   // largest opt-in so far, per device
+  const int dev = current_device();
+  if (smem > attr[dev]) {
+    if (!set_max_smem(conv3x3_strip_kernel<CO>, smem, "conv3x3_strip_kernel")) return false;
+    attr[dev] = smem;
   }
   conv3x3_strip_kernel<CO><<<dim3(ceil_div(h, th), b), kStripThreads, smem, st>>>(
       x, x_bs, xa, xa_bs, weight, bias, res, res_bs, y, y_bs, cin, h, w, cout, th, relu);
@@ -330,14 +331,12 @@ extern "C" int otp_conv2d(const float *x, long long x_bstride, const float *x_ad
     return check_launch("conv1x1_vec_kernel");
   }
   if (k == 1) {
-    if (smem > 48 * 1024)
-      cudaFuncSetAttribute(conv2d_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 48 * 1024 && !set_max_smem(conv2d_kernel<1>, smem, "conv2d_kernel")) return OTP_ERR_CUDA;
     conv2d_kernel<1><<<grid, kCvThreads, smem, st>>>(x, x_bstride, x_add, x_add_bstride, weight, bias,
                                                       residual, residual_bstride, y, y_bstride, cin, h,
                                                       w, cout, dilation, relu);
   } else {
-    if (smem > 48 * 1024)
-      cudaFuncSetAttribute(conv2d_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 48 * 1024 && !set_max_smem(conv2d_kernel<3>, smem, "conv2d_kernel")) return OTP_ERR_CUDA;
     conv2d_kernel<3><<<grid, kCvThreads, smem, st>>>(x, x_bstride, x_add, x_add_bstride, weight, bias,
                                                       residual, residual_bstride, y, y_bstride, cin, h,
                                                       w, cout, dilation, relu);

@@ -325,18 +325,19 @@ extern "C" int otp_conv2d_tc(const float *x, long long x_bstride, const float *x
   const ConvTcShape S = conv_tc_shape(cin, cout, k, w);
   const int tiles = ceil_div(h * w, kCtTM);
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_done = false;
-  if (!attr_done) {
-    const int lim = 100 * 1024;
-#define OTP_CONV_ATTR(U, M, NT)                                                                                   \
-  cudaFuncSetAttribute(conv_tc_kernel<true, U, M, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);         \
-  cudaFuncSetAttribute(conv_tc_kernel<false, U, M, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)
+  static PerDeviceOnce attr;
+  if (attr.first()) {
+    const size_t lim = 100 * 1024;
+    bool ok = true;
+#define OTP_CONV_ATTR(U, M, NT)                                                        \
+  ok = ok && set_max_smem(conv_tc_kernel<true, U, M, NT>, lim, "conv_tc_kernel") &&    \
+       set_max_smem(conv_tc_kernel<false, U, M, NT>, lim, "conv_tc_kernel")
     OTP_CONV_ATTR(3, 6, 128);
     OTP_CONV_ATTR(5, 4, 128);
     OTP_CONV_ATTR(5, 2, 256);
     OTP_CONV_ATTR(6, 2, 256);
 #undef OTP_CONV_ATTR
-    attr_done = true;
+    if (!ok) return OTP_ERR_CUDA;
   }
   LaunchScope ls(K_CONV2D, st);
   const uint8_t *pk = static_cast<const uint8_t *>(packed);

@@ -322,11 +322,11 @@ extern "C" int otp_offset_mask_dcn_forward(const void *packed, const float *tran
   OTP_REQUIRE(packed && trans && x && dcn_w && out);
   cudaStream_t st = (cudaStream_t)stream;
   const bool f16 = precision == OTP_PREC_FP16;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(tc_dcn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
-    cudaFuncSetAttribute(tc_dcn_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
-    attr_done = true;
+  static PerDeviceOnce attr;
+  if (attr.first()) {
+    if (!set_max_smem(tc_dcn_fused_kernel<true>, kSmem, "tc_dcn_fused_kernel") ||
+        !set_max_smem(tc_dcn_fused_kernel<false>, kSmem, "tc_dcn_fused_kernel"))
+      return OTP_ERR_CUDA;
   }
   const int tiles = ceil_div(h * w, kTM);
   const int grid = b * tiles < num_sms() ? b * tiles : num_sms();

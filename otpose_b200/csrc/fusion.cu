@@ -303,14 +303,12 @@ extern "C" int otp_pyramid_conv1x1(const float *s0, const float *s1, const float
   LaunchScope ls(K_PYRAMID, st);
   if (cout % 17 == 0) {
     size_t smem = (size_t)3 * c * 20 * sizeof(float);
-    if (smem > 48 * 1024)
-      cudaFuncSetAttribute(pyramid_conv_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 48 * 1024 && !set_max_smem(pyramid_conv_kernel<17>, smem, "pyramid_conv_kernel")) return OTP_ERR_CUDA;
     pyramid_conv_kernel<17><<<dim3(ceil_div(t, 2 * kFuThreads), b, cout / 17), kFuThreads, smem, st>>>(
         s0, s1, s2, c, t, t1, t2, weight, bias, cout, out, out_bstride);
   } else {
     size_t smem = (size_t)3 * c * 16 * sizeof(float);
-    if (smem > 48 * 1024)
-      cudaFuncSetAttribute(pyramid_conv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 48 * 1024 && !set_max_smem(pyramid_conv_kernel<16>, smem, "pyramid_conv_kernel")) return OTP_ERR_CUDA;
     pyramid_conv_kernel<16><<<dim3(ceil_div(t, 2 * kFuThreads), b, ceil_div(cout, 16)), kFuThreads, smem, st>>>(
         s0, s1, s2, c, t, t1, t2, weight, bias, cout, out, out_bstride);
   }

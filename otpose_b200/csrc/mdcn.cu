@@ -102,8 +102,7 @@ static int launch_mdcn(const float *x, const float *offset, const float *mask, c
     set_error("otp_mdcn_forward: weight tile of %zu B does not fit shared memory", smem);
     return OTP_ERR_UNSUPPORTED;
   }
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(mdcn_fwd_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (smem > 48 * 1024 && !set_max_smem(mdcn_fwd_kernel<CO>, smem, "mdcn_fwd_kernel")) return OTP_ERR_CUDA;
   dim3 grid(ceil_div(ho * wo, kDcnThreads), b, ceil_div(cout, CO));
   LaunchScope ls(K_MDCN, st);
   mdcn_fwd_kernel<CO><<<grid, kDcnThreads, smem, st>>>(x, offset, mask, weight, bias, out, c, h, w,

@@ -206,11 +206,8 @@ extern "C" int otp_mdcn_backward(const float *x, const float *offset, const floa
   float *gw_part = reinterpret_cast<float *>(ws + s.gw_part);
   float *gb_part = reinterpret_cast<float *>(ws + s.gb_part);
   cudaMemsetAsync(gx_fix, 0, (size_t)b * c * h * w * 8, st);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(mdcn_bwd_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
-  }
+  static PerDeviceOnce attr;
+  if (attr.first() && !set_max_smem(mdcn_bwd_kernel<17>, 200 * 1024, "mdcn_bwd_kernel")) return OTP_ERR_CUDA;
   {
     LaunchScope ls(K_MDCN_BWD, st);
     mdcn_bwd_kernel<17><<<dim3(s.ncta_x, b), kBwThreads, s.smem, st>>>(

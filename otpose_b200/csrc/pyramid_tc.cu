@@ -245,11 +245,11 @@ extern "C" int otp_pyramid_conv1x1_tc(const float *s0, const float *s1, const fl
   const PyShape S = py_shape(c);
   const int tiles = ceil_div(t, kPyTM);
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(pyramid_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(pyramid_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
+  static PerDeviceOnce attr;
+  if (attr.first()) {
+    if (!set_max_smem(pyramid_tc_kernel<true>, 200 * 1024, "pyramid_tc_kernel") ||
+        !set_max_smem(pyramid_tc_kernel<false>, 200 * 1024, "pyramid_tc_kernel"))
+      return OTP_ERR_CUDA;
   }
   LaunchScope ls(K_PYRAMID, st);
   const int grid = min(b * tiles, num_sms());

@@ -283,6 +283,8 @@ class OTPose(nn.Module):
                 self._forward_head_eager(s_rough, s_margin)
                 self._forward_head_eager(s_rough, s_margin)
             torch.cuda.current_stream(dev).wait_stream(warm)
+            warm.synchronize()
+            _lib.workspace.drop_stream(dev, warm)         # the warm-up stream's scratch buffers are not kept
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 outs = self._forward_head_eager(s_rough, s_margin)

@@ -433,9 +433,7 @@ def test_upsample_matches_torch():
 # ----------------------------------------------------------------- a7 RSB
 @pytest.mark.parametrize("name,cin,cout", [("rsb_def_fuse", 17, 17), ("rsb_combine", 51, 32)])
 def test_rsb_vs_reference_golden(name, cin, cout):
-    """RSB chains stay on the fp32 CUDA-core convs in every precision mode (a tcgen05 implicit-GEMM
-    variant was measured slower at these 6..20-channel widths: the per-element im2col overhead
-    exceeds the FMA loop it replaces)."""
+    """fp32 mode (CUDA-core convs; also the path of maps whose width is not a multiple of 8)."""
     g = golden(name)
     m = CHAIN_RSB_BLOCKS(cin, cout, 2)
     m.load_state_dict(syn.fill_state_dict(manifest()[name], seed=int(g["seed"])))
@@ -444,6 +442,23 @@ def test_rsb_vs_reference_golden(name, cin, cout):
     x = cuda(np.random.default_rng(4).standard_normal((3, cin, 50, 37)).astype(np.float32))   # ragged strips
     ref = ho.chain_rsb({k: v.cpu() for k, v in m.state_dict().items()}, "", x.cpu(), 2)
     assert rel(m(x), ref) < 1e-4
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("fp16", 5e-3), ("bf16", BF16_TOL)])
+def test_rsb_w8_vs_reference_golden(precision, tol):
+    """Reference-generated fixture with W % 8 == 0: in the 16-bit modes every conv of the chain runs
+    on the tcgen05 implicit-GEMM kernel (conv_tc.cu)."""
+    g = golden("rsb_combine_w8")
+    m = CHAIN_RSB_BLOCKS(51, 32, 2)
+    m.load_state_dict(syn.fill_state_dict(manifest()["rsb_combine_w8"], seed=int(g["seed"])))
+    m = m.cuda().eval()
+    for mod in m.modules():
+        if hasattr(mod, "precision"):
+            mod.precision = precision
+    lib = _lib.load()
+    if precision != "fp32":
+        assert lib.otp_conv2d_tc_supported(20, 20, g["x"].shape[2], g["x"].shape[3], 3) == 1
+    assert rel(m(cuda(g["x"])), g["out"]) < tol
 
 
 # ----------------------------------------------------------------- whole head
@@ -457,8 +472,8 @@ def build_head(h, w, precision, seed=2024):
 NAMES = ("output_heatmaps", "rough_heatmaps", "intersection", "prev_b", "context_encoding", "squeezed", "total_b")
 
 
-@pytest.mark.parametrize("name,b,h,w", [("head_16x12", 2, 16, 12), ("head_24x20", 1, 24, 20)])
-@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("name,b,h,w", [("head_16x12", 2, 16, 12), ("head_24x20", 1, 24, 20), ("head_16x16", 1, 16, 16)])
+@pytest.mark.parametrize("precision", ["fp32", "fp16", "bf16"])
 def test_head_vs_reference_forward_golden(name, b, h, w, precision):
     g = golden(name)
     model, _ = build_head(h, w, precision, seed=int(g["seed"]))
@@ -472,10 +487,21 @@ def test_head_vs_reference_forward_golden(name, b, h, w, precision):
         assert rel(o, g[n]) < TOL[precision], n
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def index_agreement(idx, ref_idx, ref_heatmaps):
+    """Fraction of (clip, joint) arg-max indices equal to the oracle's, and the worst relative height
+    deficit of a disagreeing pick on the ORACLE's map (0 = a tie in value)."""
+    agree = idx == ref_idx
+    flat = ref_heatmaps.reshape(idx.shape[0], idx.shape[1], -1)
+    picked = np.take_along_axis(flat, idx[..., None].astype(np.int64), 2)[..., 0]
+    best = flat.max(2)
+    deficit = float(((best - picked) / np.maximum(np.abs(best), 1e-30)).max())
+    return float(agree.mean()), deficit
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16", "bf16"])
 def test_head_full_size_vs_oracle(precision):
     """BASELINE config 1: batch 1, 5 frames, 96x72, 17 joints.  fp32 mode <= 1e-3; the 16-bit
-    tensor-core mode (IEEE-half operands, fp32 accumulate) <= 2e-2."""
+    tensor-core modes (fp32 accumulate) <= 2e-2 on every output."""
     b, h, w = 1, 96, 72
     model, sd = build_head(h, w, precision)
     rough = syn.synth_rough_heatmaps(b, 17, h, w)
@@ -486,14 +512,20 @@ def test_head_full_size_vs_oracle(precision):
         if n == "rough_heatmaps":
             continue
         assert rel(o, r) < TOL[precision], n
-    # key points from the refined heat maps: indices bit-exact in fp32 mode
+    # key points: the arg-max kernel is bit-exact on the maps it is given (all modes) ...
     center, scale = syn.synth_center_scale(b)
     got = hm_mod.final_preds_cuda(outs[0], cuda(center), cuda(scale))
     idx, coords, preds, maxvals = ho.final_preds_full(outs[0].cpu().numpy(), center, scale)
     assert np.array_equal(got["idx"].cpu().numpy(), idx)
+    # ... and against the ORACLE's heat maps: identical in fp32 mode; in the 16-bit modes an index may move
+    # only between pixels whose oracle heights differ by less than the mode's tolerance
+    ridx = ho.final_preds_full(ref[0].numpy(), center, scale)[0]
+    frac, deficit = index_agreement(got["idx"].cpu().numpy(), ridx, ref[0].numpy())
+    print(f"[{precision}] arg-max index agreement vs the oracle's heat maps: {frac:.4f}, worst height deficit {deficit:.2e}")
     if precision == "fp32":
-        ridx = ho.final_preds_full(ref[0].numpy(), center, scale)[0]
-        assert np.array_equal(got["idx"].cpu().numpy(), ridx)
+        assert frac == 1.0
+    else:
+        assert deficit < 2 * TOL[precision]
 
 
 @pytest.mark.parametrize("frames,precision", [(3, "fp16"), (5, "fp32"), (5, "fp16"), (7, "fp16")])
@@ -516,14 +548,15 @@ def test_head_config5_window_sweep_128x96(frames, precision):
     assert np.array_equal(got["idx"].cpu().numpy(), ho.final_preds_full(outs[0].cpu().numpy(), center, scale)[0])
 
 
-def test_bf16_operand_variant_documented_accuracy():
-    """The same tensor-core kernels with bfloat16 operands (8-bit significand).  Encoder
-    features stay inside the 2e-2 bar (test_encoder_*[bf16]); the refined heat maps do NOT:
-    the final 1x1 conv and the learned-offset DCN sampling amplify the 1.3e-2 feature error
-    to ~2.7e-2 at 96x72 (more on tiny maps, where dilation 15 exceeds the map).  The variant
-    is an option, not the mode of record (that is "fp16": 3e-3 on the same tensor); this test
-    pins its measured level so a regression is still caught."""
-    b, h, w = 1, 96, 72
+@pytest.mark.parametrize("h,w", [(96, 72), (128, 96)])
+def test_bf16_operand_mode_meets_the_bar(h, w):
+    """precision="bf16" (bfloat16 tensor-core operands) meets 2e-2 on EVERY output at both bench map sizes.
+    bfloat16 rounding of the WEIGHTS is a systematic (token-coherent) perturbation, which the channel Gram
+    accumulates over all tokens; the mode therefore (a) never rounds W_q / W_k (they are applied in fp32 to
+    the token-reduced Gram, block_fold.cuh) and (b) carries the MLP / proj / final-layer / offset-conv
+    weights as two bfloat16 terms (hi + lo, one extra UMMA chain).  scripts/emulate_operand_rounding.py
+    attributes the error site by site."""
+    b = 1
     model, sd = build_head(h, w, "bf16")
     rough, margin = syn.synth_rough_heatmaps(b, 17, h, w), syn.synth_margin(b)
     ref = ho.head_forward(sd, rough, margin)
@@ -531,7 +564,7 @@ def test_bf16_operand_variant_documented_accuracy():
     for n, o, r in zip(NAMES, outs, ref):
         if n == "rough_heatmaps":
             continue
-        assert rel(o, r) < (5e-2 if n == "output_heatmaps" else BF16_TOL), n
+        assert rel(o, r) < BF16_TOL, (n, rel(o, r))
 
 
 def test_head_batch_consistency_full_batch():
@@ -569,6 +602,29 @@ def test_head_cuda_graph_replay_matches_eager():
         assert torch.equal(o, e), n
     model.load_state_dict(sd)          # parameters replaced -> graphs dropped
     assert len(model._graphs) == 0
+
+
+def test_head_cuda_graphs_of_two_shapes_do_not_share_scratch():
+    """A graph captured for a small batch keeps working after a LARGER batch was captured and run, and
+    after an eager call regrew the pooled workspaces (each capture owns its scratch buffers: they are
+    allocated inside the capture, in the graph's private pool -- _lib._WorkspacePool)."""
+    h, w = 24, 16
+    model, _ = build_head(h, w, "fp16")
+    ins = {b: (syn.synth_rough_heatmaps(b, 17, h, w, seed=b).cuda(), syn.synth_margin(b, seed=b + 1).cuda())
+           for b in (1, 6)}
+    eager = {b: model.forward_head(*ins[b])[0].clone() for b in (1, 6)}
+    model.cuda_graph = True
+    assert torch.equal(model.forward_head(*ins[1])[0], eager[1])       # capture shape A
+    assert torch.equal(model.forward_head(*ins[6])[0], eager[6])       # capture the larger shape B
+    model.cuda_graph = False
+    _lib.workspace.clear()
+    big = (syn.synth_rough_heatmaps(9, 17, h, w, seed=3).cuda(), syn.synth_margin(9, seed=4).cuda())
+    model.forward_head(*big)                                           # eager, regrows every pooled buffer
+    torch.cuda.empty_cache()
+    model.cuda_graph = True
+    assert len(model._graphs) == 2
+    for b in (1, 6, 1):                                                # replay A after B (and back)
+        assert torch.equal(model.forward_head(*ins[b])[0], eager[b]), b
 
 
 def test_head_from_backbone_features_a0():

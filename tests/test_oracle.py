@@ -38,7 +38,7 @@ def test_encoder_matches_reference(golden_dir, name):
         assert relmax(o.numpy(), g[f"out{i}"]) < 1e-5
 
 
-@pytest.mark.parametrize("name", ["rsb_def_fuse", "rsb_combine"])
+@pytest.mark.parametrize("name", ["rsb_def_fuse", "rsb_combine", "rsb_combine_w8"])
 def test_rsb_matches_reference(golden_dir, name):
     g = load(golden_dir, name)
     sd = syn.fill_state_dict(manifest(golden_dir)[name], seed=int(g["seed"]))
@@ -53,7 +53,7 @@ def head_state_dict(golden_dir, h, w, seed):
     return syn.fill_state_dict(shapes, seed=seed)
 
 
-@pytest.mark.parametrize("name,b,h,w", [("head_16x12", 2, 16, 12), ("head_24x20", 1, 24, 20)])
+@pytest.mark.parametrize("name,b,h,w", [("head_16x12", 2, 16, 12), ("head_24x20", 1, 24, 20), ("head_16x16", 1, 16, 16)])
 def test_head_matches_reference_forward(golden_dir, name, b, h, w):
     g = load(golden_dir, name)
     sd = head_state_dict(golden_dir, h, w, int(g["seed"]))
