@@ -42,7 +42,16 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="person-clips per GPU per step")
+    ap.add_argument("--batch", type=int, default=32,
+                    help="person-clips per forward call (= per GPU per step unless --total-clips is given)")
+    ap.add_argument("--total-clips", type=int, default=0,
+                    help="BASELINE configs[2]: a FIXED total of clips per step split over the ranks (strong scaling, "
+                         "e.g. 512 -> 512/256/128/64 per GPU), each rank running its shard as forward calls of "
+                         "--batch clips")
+    ap.add_argument("--no-full-inference", action="store_true",
+                    help="skip the BASELINE configs[1] leg (HRNet-W48 backbone + head, N=1 only)")
+    ap.add_argument("--roofline-seconds", type=float, default=2.2,
+                    help="minimum GPU time of the per-kernel (roofline) pass, so that the sustained peak applies")
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16", "fp16"])
     ap.add_argument("--cpu-clips", type=int, default=2, help="clips per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -216,15 +225,113 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(batch, precision):
+def workload_config(batch, precision, total=0, world=1, call=None):
+    shard = f"{total} person-clips per step split over {world} GPU(s) = {batch} per GPU, forward calls of {call} clips" \
+        if total else f"{batch} person-clips/GPU"
     return {"workload": f"OTPose temporal head fwd (fusion prologue + flow/temporal ConvTransformer encoders + "
-                        f"RSB + 5x offset/mask conv + modulated DCN + get_final_preds), {batch} person-clips/GPU, "
-                        f"{FRAMES} frames, {H}x{W} heat maps, {J} joints (BASELINE configs[1] batch; HRNet backbone out of scope)",
+                        f"RSB + 5x offset/mask conv + modulated DCN + get_final_preds), {shard}, "
+                        f"{FRAMES} frames, {H}x{W} heat maps, {J} joints "
+                        f"({'BASELINE configs[2]' if total else 'BASELINE configs[1] batch'}; the HRNet backbone is "
+                        f"timed separately in `full_inference`)",
             "clips_per_gpu": batch, "heatmap": [H, W], "joints": J, "precision": precision,
             "l2": "per-step working set (activations > 1 GB at 32 clips) far exceeds the 126 MB L2; no explicit flush"}
 
 
 # ----------------------------------------------------------------------------------------
+def kernel_source_sha(kernel):
+    """sha256 (12 hex digits) of the CUDA sources a kernel of the per-kernel table is built from: an ncu
+    traffic record (profiles/r02_traffic.json) is only quoted while it matches the code that is running."""
+    import hashlib
+    files = {"tc_block_back": ["block_tc_back.cuh", "block_tc.cu", "tc_common.cuh"],
+             "tc_block_front": ["block_tc_front.cuh", "block_tc.cu", "tc_common.cuh"],
+             "tc_block_apply": ["block_tc.cu", "tc_common.cuh"],
+             "tc_offset_mask_dcn": ["dcn_tc.cu", "tc_common.cuh"], "conv2d": ["conv_tc.cu", "conv2d.cu", "tc_common.cuh"]}
+    h = hashlib.sha256()
+    for f in files.get(kernel, []):
+        try:
+            with open(os.path.join(ROOT, "otpose_b200", "csrc", f), "rb") as fh:
+                h.update(fh.read())
+        except OSError:
+            return None
+    return h.hexdigest()[:12] if kernel in files else None
+
+
+def measured_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the round's committed `ncu --set full` capture, or None when
+    there is no record for the code as it is now (the record carries the source hash it was taken on)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            rec = json.load(f).get(kernel)
+    except Exception:
+        return None
+    if not rec or rec.get("source_sha") != kernel_source_sha(kernel):
+        return None
+    return rec.get("dram_bytes_per_launch")
+
+
+def full_inference(args, model, dev, precision):
+    """BASELINE configs[1]: HRNet-W48 backbone (torch / cuDNN, Conv+BN folded, channels-last bf16, CUDA graph)
+    -> OTPose.forward_from_features (HRNet.final_layer fused into the head's first kernel) -> final_preds_cuda,
+    32 clips x 5 frames of 384x288 synthetic images, random-init weights.  The backbone is library code (SURVEY
+    8f rank 3); the leg exists to state the head's share of the full step."""
+    import torch
+    from otpose_b200.model.HRNet import HRNet, hrnet_w48_cfg
+    from otpose_b200.utils import heatmap, synthetic as syn
+    b = min(args.batch, 32)
+    torch.backends.cudnn.benchmark = True
+    net = HRNet(hrnet_w48_cfg(J))
+    net.load_state_dict(syn.fill_state_dict({k: v.shape for k, v in net.state_dict().items()}, seed=2025))
+    net = net.eval().to(dev)
+    fl_w, fl_b = net.final_layer.weight.detach().float(), net.final_layer.bias.detach().float()
+    folded = net.fold(dtype=torch.bfloat16, memory_format=torch.channels_last)
+    g = torch.Generator().manual_seed(1235)
+    images = torch.randn((FRAMES * b, 3, 4 * H, 4 * W), generator=g).to(dev).to(torch.bfloat16) \
+        .contiguous(memory_format=torch.channels_last)
+    margin = syn.synth_margin(b, frames=FRAMES).to(dev)
+    center, scale = (torch.from_numpy(a).to(dev) for a in syn.synth_center_scale(b))
+    with torch.no_grad():
+        for _ in range(3):
+            feats = folded.features(images)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            feats = folded.features(images)
+
+    def head(f):
+        out = model.forward_from_features(f, margin, weight=fl_w, bias=fl_b)[0]
+        return heatmap.final_preds_cuda(out, center, scale)
+
+    def step():
+        graph.replay()
+        return head(feats)
+
+    def timed(fn, n):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    for _ in range(3):
+        r = step()
+    n = max(3, min(args.steps, 10))
+    ms_full = timed(step, n)
+    ms_backbone = timed(graph.replay, n)
+    ms_head = timed(lambda: head(feats), n)
+    assert bool(torch.isfinite(r["preds"]).all())
+    return {"config": f"full OTPose inference: HRNet-W48 backbone (cuDNN, Conv+BN folded, channels-last bf16, CUDA "
+                      f"graph; random init) + temporal head ({precision} operands, HRNet.final_layer fused into the "
+                      f"head) + get_final_preds, {b} clips x {FRAMES} frames of {4 * H}x{4 * W} synthetic images, 1 GPU",
+            "clips_per_s": round(b / (ms_full * 1e-3), 1), "ms_per_step": round(ms_full, 3),
+            "backbone_ms": round(ms_backbone, 3), "head_ms": round(ms_head, 3),
+            "head_share_of_step": round(ms_head / (ms_backbone + ms_head), 4), "steps": n,
+            "backbone_tflops": round(353.07e9 * b * (H * W) / T / (ms_backbone * 1e-3) / 1e12, 1),
+            "note": "backbone = library (cuDNN) code, BASELINE.md section 3: 353 GFLOP/clip; head = this library"}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -241,56 +348,74 @@ def run_b200(args):
     precision = args.precision
     if precision == "auto":
         precision = "fp16" if lib.otp_has_tensor_core_path() else "fp32"
-    b = args.batch
+    # clips of this rank per step, and how they are cut into forward calls
+    if args.total_clips:
+        if args.total_clips % world:
+            raise SystemExit(f"--total-clips {args.total_clips} is not divisible by {world} ranks")
+        b = args.total_clips // world
+    else:
+        b = args.batch
+    call = min(args.batch, b)
+    sizes = [call] * (b // call) + ([b % call] if b % call else [])
 
     model = OTPose(default_cfg((H, W)), precision=precision, cuda_graph=not args.no_cuda_graph)
     model.load_state_dict(syn.fill_state_dict({k: v.shape for k, v in model.state_dict().items()}, seed=2024))
     model = model.to(dev).eval()
-    rough_host = syn.synth_rough_heatmaps(b, J, H, W, frames=FRAMES, seed=shard_seed(1234, rank)).pin_memory()
-    margin_host = syn.synth_margin(b, seed=shard_seed(1236, rank), frames=FRAMES).pin_memory()
-    center, scale = (torch.from_numpy(a).to(dev) for a in syn.synth_center_scale(b, seed=shard_seed(1237, rank)))
-    rough, margin = rough_host.to(dev), margin_host.to(dev)
-    rough_stage = torch.empty_like(rough)
-    margin_stage = torch.empty_like(margin)
-    preds_host = torch.empty((b, J, 2), dtype=torch.float32).pin_memory()
-    vals_host = torch.empty((b, J, 1), dtype=torch.float32).pin_memory()
+    # every forward call of a step has its own synthetic clips (seeded per rank and call), resident on the
+    # device for `value`, in pinned host memory for `e2e`
+    hosts, resident, cs = [], [], []
+    for ci, n in enumerate(sizes):
+        sd = 37 * ci
+        hosts.append((syn.synth_rough_heatmaps(n, J, H, W, frames=FRAMES, seed=shard_seed(1234 + sd, rank)).pin_memory(),
+                      syn.synth_margin(n, seed=shard_seed(1236 + sd, rank), frames=FRAMES).pin_memory()))
+        resident.append(tuple(t.to(dev) for t in hosts[-1]))
+        cs.append(tuple(torch.from_numpy(a).to(dev) for a in syn.synth_center_scale(n, seed=shard_seed(1237 + sd, rank))))
+    preds_host = [torch.empty((n, J, 2), dtype=torch.float32).pin_memory() for n in sizes]
+    vals_host = [torch.empty((n, J, 1), dtype=torch.float32).pin_memory() for n in sizes]
 
     def step_resident():
-        out = model.forward_head(rough, margin)[0]
-        return heatmap.final_preds_cuda(out, center, scale)
+        for (rough, margin), (center, scale) in zip(resident, cs):
+            out = model.forward_head(rough, margin)[0]
+            r = heatmap.final_preds_cuda(out, center, scale)
+        return r
 
-    # end to end through the public API: every step copies ITS inputs from pinned host memory and
-    # reads its result back.  Double-buffered: the copy of step i+1 runs on a copy stream while step i
+    # end to end through the public API: every forward call copies ITS inputs from pinned host memory and
+    # reads its result back.  Double-buffered: the copy of call i+1 runs on a copy stream while call i
     # computes (forward_head is asynchronous on the caller's stream), as a serving loop would do.
     copy_stream = torch.cuda.Stream(device=dev)
-    stages = [(rough_stage, margin_stage), (torch.empty_like(rough), torch.empty_like(margin))]
+    big = max(range(len(sizes)), key=lambda k: sizes[k])
+    stages = [tuple(torch.empty_like(t) for t in resident[big]) for _ in range(2)]
     ev_ready = [torch.cuda.Event(), torch.cuda.Event()]
     ev_free = [torch.cuda.Event(), torch.cuda.Event()]
     e2e_state = {"i": 0}
+    ncall = len(sizes)
 
-    def issue_copy(slot):
+    def issue_copy(slot, ci):
+        n = sizes[ci]
         with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(ev_free[slot])      # the step that last used this slot has consumed it
-            stages[slot][0].copy_(rough_host, non_blocking=True)
-            stages[slot][1].copy_(margin_host, non_blocking=True)
+            copy_stream.wait_event(ev_free[slot])      # the call that last used this slot has consumed it
+            stages[slot][0][:FRAMES * n].copy_(hosts[ci][0], non_blocking=True)
+            stages[slot][1][:n].copy_(hosts[ci][1], non_blocking=True)
             ev_ready[slot].record(copy_stream)
 
     def step_e2e():
         main = torch.cuda.current_stream(dev)
-        i = e2e_state["i"]
-        slot = i & 1
-        if i == 0:
-            ev_free[0].record(main)
-            ev_free[1].record(main)
-            issue_copy(0)
-        issue_copy(slot ^ 1)                           # next step's inputs, overlapped with this step
-        main.wait_event(ev_ready[slot])
-        out = model.forward_head(stages[slot][0], stages[slot][1])[0]
-        ev_free[slot].record(main)
-        r = heatmap.final_preds_cuda(out, center, scale)
-        preds_host.copy_(r["preds"], non_blocking=True)
-        vals_host.copy_(r["maxvals"], non_blocking=True)
-        e2e_state["i"] = i + 1
+        for ci in range(ncall):
+            i = e2e_state["i"]
+            slot = i & 1
+            if i == 0:
+                ev_free[0].record(main)
+                ev_free[1].record(main)
+                issue_copy(0, ci)
+            issue_copy(slot ^ 1, (ci + 1) % ncall)     # next call's inputs, overlapped with this call
+            main.wait_event(ev_ready[slot])
+            n = sizes[ci]
+            out = model.forward_head(stages[slot][0][:FRAMES * n], stages[slot][1][:n])[0]
+            ev_free[slot].record(main)
+            r = heatmap.final_preds_cuda(out, cs[ci][0], cs[ci][1])
+            preds_host[ci].copy_(r["preds"], non_blocking=True)
+            vals_host[ci].copy_(r["maxvals"], non_blocking=True)
+            e2e_state["i"] = i + 1
 
     def barrier():
         if world > 1:
@@ -316,16 +441,18 @@ def run_b200(args):
     launches0 = lib.otp_launch_count()
     ms = timed(step_resident, args.steps)          # the headline: no per-kernel events in the timed region
     launches = lib.otp_launch_count() - launches0
-    # per-kernel table / roofline: a second pass of the same K steps with the library's CUDA events
-    # around every launch (2 events x ~190 launches per step cost ~7 % of the step, hence separate)
+    # per-kernel table / roofline: a second pass with the library's CUDA events around every launch (2 events
+    # x ~190 launches per step cost ~7 % of the step, hence separate), run for at least --roofline-seconds
+    # of GPU time so that the SUSTAINED tensor peak is the right denominator
     graph_mode = model.cuda_graph
     model.cuda_graph = False                       # per-kernel events need the individual launches,
     model.overlap_branches = False                 # one after the other (no side-stream overlap)
     lib.otp_profile_enable(1)
     launches1 = lib.otp_launch_count()
-    ms_profiled = timed(step_resident, args.steps)
+    psteps = max(args.steps, min(2000, int(args.roofline_seconds * 1e3 / max(ms / args.steps, 1e-3)) + 1))
+    ms_profiled = timed(step_resident, psteps)
     if graph_mode:   # the timed region replayed these same kernels as graph nodes: count them here
-        launches = lib.otp_launch_count() - launches1
+        launches = (lib.otp_launch_count() - launches1) * args.steps // psteps
     model.cuda_graph = graph_mode
     model.overlap_branches = True
     prof = _lib.profile_read()
@@ -341,8 +468,8 @@ def run_b200(args):
         work = algorithmic_work(b, t=H * W, precision=precision)
         kernels = {}
         for name, (tot_ms, cnt) in prof.items():
-            per_step = tot_ms / args.steps
-            k = {"ms_per_step": round(per_step, 4), "launches_per_step": cnt / args.steps}
+            per_step = tot_ms / psteps
+            k = {"ms_per_step": round(per_step, 4), "launches_per_step": cnt / psteps}
             if name in work and per_step > 0:
                 bound, amount = work[name]
                 ach = amount / (per_step * 1e-3) / (1e12 if bound == "tensor" else 1e9)
@@ -351,33 +478,36 @@ def run_b200(args):
             kernels[name] = k
         top = max((n for n in kernels if "bound" in kernels[n]), key=lambda n: kernels[n]["ms_per_step"])
         tk = kernels[top]
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get(top)
-        except Exception:
-            pass
         roofline = {"kernel": top, "bound": tk["bound"], "achieved": tk["achieved"], "peak": peaks[tk["bound"]],
-                    "unit": tk["unit"], "frac": tk["frac"], "traffic": traffic,
+                    "unit": tk["unit"], "frac": tk["frac"], "traffic": measured_traffic(top),
+                    "traffic_source": "profiles/r02_traffic.json (ncu --set full, keyed by the kernel's source hash "
+                                      f"{kernel_source_sha(top)}; null = no capture of the code as built)",
                     "peak_source": f"{peaks['source']} ({'sustained bf16' if tk['bound'] == 'tensor' else 'copy'})",
                     "share_of_step": round(tk["ms_per_step"] / sum(k["ms_per_step"] for k in kernels.values()), 4),
-                    "timing": "CUDA events around every launch of this kernel in a separate pass of the same "
-                              f"{args.steps} steps ({ms_profiled / args.steps:.3f} ms/step with events)"}
-        line = {"metric": METRIC, "value": b * world * args.steps / (ms * 1e-3), "unit": "clips/s",
+                    "timing": "CUDA events around every launch of this kernel in a separate pass of "
+                              f"{psteps} steps = {ms_profiled * 1e-3:.2f} s ({ms_profiled / psteps:.3f} ms/step with events)"}
+        total = b * world
+        line = {"metric": METRIC, "value": total * args.steps / (ms * 1e-3), "unit": "clips/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong" if args.total_clips else "weak", "vs_baseline": None,
                 "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[precision], "data": "synthetic",
-                "config": dict(workload_config(b, precision),
-                               launch="OTPose(cuda_graph=True): one captured CUDA graph replay per step"
+                "config": dict(workload_config(b, precision, args.total_clips, world, call),
+                               launch="OTPose(cuda_graph=True): one captured CUDA graph replay per forward call"
                                if model.cuda_graph else "eager: one launch per kernel"), "clocks": clocks,
-                "e2e": {"value": b * world * args.steps / (ms_e2e * 1e-3), "unit": "clips/s",
-                        "h2d_bytes_per_step": rough_host.numel() * 4 + margin_host.numel() * 8,
-                        "d2h_bytes_per_step": preds_host.numel() * 4 + vals_host.numel() * 4,
+                "e2e": {"value": total * args.steps / (ms_e2e * 1e-3), "unit": "clips/s",
+                        "h2d_bytes_per_step": sum(h[0].numel() * 4 + h[1].numel() * 8 for h in hosts),
+                        "d2h_bytes_per_step": sum(p.numel() * 4 for p in preds_host) + sum(v.numel() * 4 for v in vals_host),
                         "ms_per_step": ms_e2e / args.steps,
-                        "pipeline": "double-buffered: step i+1's pinned-host -> device copy runs on a copy stream "
-                                    "while step i computes; every step's copy and result read-back are inside "
+                        "pipeline": "double-buffered: call i+1's pinned-host -> device copy runs on a copy stream "
+                                    "while call i computes; every call's copy and result read-back are inside "
                                     "the timed region"},
                 "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels}
+        if world == 1 and not args.no_full_inference and (H, W) == (96, 72) and FRAMES == 5:
+            try:
+                line["full_inference"] = full_inference(args, model, dev, precision)
+            except Exception as e:      # the secondary leg must never cost the headline line
+                line["full_inference"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference(args.cpu_clips, 3, 1)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -8,6 +8,8 @@ test-suite only read the committed vectors.  What is executed unmodified:
   ``model/RSB.py`` CHAIN_RSB_BLOCKS                     (imported as-is)
 * ``model/OTPose.py`` OTPose.__init__/forward lines 307-394 (imported as-is)
 * ``utils/heatmap.py`` get_max_preds / get_final_preds, ``utils/transform.py``
+* ``model/HRNet.py`` HRNet (the W48 backbone of configs[1]; constructor config =
+  configs/Base_PoseTrack17.yaml:46-88)
 
 What has to be shimmed, and how (nothing below changes arithmetic on the path):
 
@@ -161,6 +163,16 @@ def main():
                  "squeezed", "total_b")
         save(name, seed=2024, rough_seed=1234, margin_seed=1236, margin=margin,
              **{n: o for n, o in zip(names, outs) if n != "rough_heatmaps"})
+
+    # ---- HRNet-W48 backbone (reference model/HRNet.py, imported as-is) -------
+    from model.HRNet import HRNet as RefHRNet
+    from otpose_b200.model.HRNet import hrnet_w48_cfg
+    net = RefHRNet(hrnet_w48_cfg()).eval()
+    sh = shapes_of(net)
+    manifest["hrnet"] = {k: list(v) for k, v in sh.items()}
+    net.load_state_dict(syn.fill_state_dict(sh, seed=2024))
+    img = torch.from_numpy(np.random.default_rng(31).standard_normal((1, 3, 64, 64)).astype(np.float32))
+    save("hrnet_w48_64x64", x=img, seed=2024, out=net(img))
 
     # ---- get_final_preds / get_max_preds (reference numpy code + cv2) --------
     hm = syn.synth_rough_heatmaps(3, 17, 24, 18, frames=1, seed=77).numpy()

@@ -51,29 +51,37 @@ constexpr uint32_t kW2c = (kKP / 8) * kRS96;       // 13824  [144][48]
 constexpr uint32_t kHTile = (kTM / 8) * kRS96;     // 12288  [128][48]
 
 // ---- packed tensor-core weights of one block (bytes) ----
+// Three operand-image sets [bf16 hi | fp16 | bf16 lo], then fp32 folded vectors / matrices.  A set holds
+// Wp, W1 chunks, W2 chunks (W1 and W2 contiguous: a chunk index addresses the same offset in every set);
+// the bf16 "lo" set holds bf16(w - bf16(w)) of the W1 / W2 images only: in bfloat16 mode tc_back runs
+// every MLP UMMA chain twice (hi, then lo into the same accumulator) because a weight's rounding error is
+// coherent across tokens (see block_tc_front.cuh; scripts/emulate_operand_rounding.py).
 struct TcPack {
-  size_t wq, wk, wp, w1 /* [6] */, w2 /* [6] */, img_bytes /* one operand format */;
-  size_t wvp /* fp32 [136][136] Wv * g_v */, bvp /* [144] */, bqp, bkp /* [144] */, b1p /* [576] */, total;
+  size_t wp, w1 /* [9] */, w2 /* [9] */, img_bytes /* one operand format */, lo /* bf16 lo set: W1, W2 only */;
+  size_t wvp /* fp32 [136][136] Wv * g_v */, bvp /* [144] */, bqp, bkp /* [144] */, b1p /* [576] */;
+  size_t wqaT, wkaT /* fp32 [144][144] transposed augmented Wq~ / Wk~ (gram_project_kernel) */, total;
 };
 constexpr TcPack tc_pack_layout() {
   TcPack p{};
-  p.wq = 0;
-  p.wk = p.wq + kW144;
-  p.wp = p.wk + kW144;
+  p.wp = 0;
   p.w1 = p.wp + kW144;
   p.w2 = p.w1 + (size_t)kNChunk * kW1c;
   p.img_bytes = p.w2 + (size_t)kNChunk * kW2c;
-  p.wvp = 2 * p.img_bytes;  // images: [bf16 set][fp16 set], then the fp32 folded vectors
+  p.lo = 2 * p.img_bytes;                         // + (offset - w1) addresses a lo chunk
+  p.wvp = p.lo + (size_t)2 * kNChunk * kW1c;
   p.bvp = p.wvp + (size_t)kC * kC * 4;
   p.bqp = p.bvp + kKP * 4;
   p.bkp = p.bqp + kKP * 4;
   p.b1p = p.bkp + kKP * 4;
-  p.total = p.b1p + kHidPad * 4;
+  p.wqaT = p.b1p + kHidPad * 4;
+  p.wkaT = p.wqaT + (size_t)kKP * kKP * 4;
+  p.total = p.wkaT + (size_t)kKP * kKP * 4;
   return p;
 }
 
+constexpr int kGramBlocks = 8;   // partial S per clip written by gram_project_kernel (== kGpBlocks)
 struct TcWorkspace {
-  size_t gram_part, beff, weff, vn, obuf, total;
+  size_t gram_part, spart, beff, weff, vn, obuf, total;
   int tiles, tiles_per_chunk, nchunk, tout;
 };
 TcWorkspace tc_workspace(int b, int t, int stride) {
@@ -89,7 +97,8 @@ TcWorkspace tc_workspace(int b, int t, int stride) {
     o += align_up(bytes, 256);
     return r;
   };
-  w.gram_part = take((size_t)b * w.nchunk * kC * kHS * 4);
+  w.gram_part = take((size_t)b * w.nchunk * kKP * kKP * 4);      // per-chunk partial G~ (137 rows used)
+  w.spart = take((size_t)b * kGramBlocks * kC * kHS * 4);        // per-column-block partial S
   w.beff = take((size_t)b * kKP * 4);
   w.weff = take((size_t)b * kW144);
   w.vn = take((size_t)b * w.tiles * kTile144);
@@ -107,7 +116,10 @@ template <bool F16>
 __device__ __forceinline__ uint32_t gelu_pair(float a, float b) {
   constexpr float kA = 0.80015708f, kB = 0.03470089f;
   if constexpr (F16) {
-    const __half2 x = __floats2half2_rn(a, b);
+    // saturating conversion: |x| > 65504 -> +-65504; from there x*x and x*p overflow to +-inf, tanh(+-inf) =
+    // +-1 and the result is x (or 0): finite for every finite input
+    const uint32_t xu = pack16x2<true>(a, b);
+    const __half2 x = *reinterpret_cast<const __half2 *>(&xu);
     const __half2 x2 = __hmul2(x, x);
     const __half2 p = __hfma2(x2, __float2half2_rn(kB), __float2half2_rn(kA));
     const __half2 t = h2tanh_approx(__hmul2(x, p));
@@ -310,8 +322,15 @@ int g_trace_on = 0;   // otp_debug_trace
 #include "block_tc_front.cuh"
 
 // ------------------------------------------------------------------ weight packing
+// 16-bit operand element of format FMT: 0 = bfloat16, 1 = IEEE half, 2 = bfloat16 remainder bf16(v - bf16(v))
+template <int FMT>
+__device__ __forceinline__ unsigned short to_fmt(float v) {
+  if constexpr (FMT == 1) return to16<true>(v);
+  if constexpr (FMT == 0) return to16<false>(v);
+  return to16<false>(v - __bfloat162float(__float2bfloat16_rn(v)));
+}
 // operand image of src[row0 + r][col0 + k] * colscale[col0 + k]   (zero padded)
-template <bool F16>
+template <int FMT>
 __global__ void pack_image_kernel(const float *__restrict__ src, int ld, int row0, int col0, int rows_valid,
                                   int cols_valid, const float *__restrict__ colscale, uint8_t *__restrict__ dst,
                                   int rows_pad, int cols_pad) {
@@ -323,16 +342,16 @@ __global__ void pack_image_kernel(const float *__restrict__ src, int ld, int row
     v = src[(size_t)(row0 + r) * ld + col0 + k];
     if (colscale) v *= colscale[col0 + k];
   }
-  *reinterpret_cast<unsigned short *>(dst + cm_offset(r, k, (cols_pad / 8) * 128, 128)) = to16<F16>(v);
+  *reinterpret_cast<unsigned short *>(dst + cm_offset(r, k, (cols_pad / 8) * 128, 128)) = to_fmt<FMT>(v);
 }
 // column `col` of an operand image <- bias[row0 + r] (r < rows_valid): the bias rides in the MMA
 // against a ones column of the activation tile
-template <bool F16>
+template <int FMT>
 __global__ void pack_bias_col_kernel(const float *__restrict__ bias, int row0, int rows_valid, uint8_t *__restrict__ dst,
                                      int cols_pad, int col) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < rows_valid)
-    *reinterpret_cast<unsigned short *>(dst + cm_offset(r, col, (cols_pad / 8) * 128, 128)) = to16<F16>(bias[row0 + r]);
+    *reinterpret_cast<unsigned short *>(dst + cm_offset(r, col, (cols_pad / 8) * 128, 128)) = to_fmt<FMT>(bias[row0 + r]);
 }
 // out[n] = bias[n] + sum_c w[n][c] * lnb[c]  (n < rows), 0 for the padding
 __global__ void fold_bias_kernel(const float *__restrict__ w, const float *__restrict__ bias,
@@ -353,12 +372,24 @@ __global__ void scale_cols_kernel(const float *__restrict__ w, const float *__re
   if (e < rows * cols) out[e] = w[e] * g[e % cols];
 }
 
-void pack_image(bool f16, const float *src, int ld, int row0, int col0, int rv, int cv, const float *colscale,
+void pack_image(int fmt, const float *src, int ld, int row0, int col0, int rv, int cv, const float *colscale,
                 uint8_t *dst, int rp, int cp, cudaStream_t st) {
-  if (f16)
-    pack_image_kernel<true><<<ceil_div(rp * cp, 256), 256, 0, st>>>(src, ld, row0, col0, rv, cv, colscale, dst, rp, cp);
+  const int g = ceil_div(rp * cp, 256);
+  if (fmt == 1)
+    pack_image_kernel<1><<<g, 256, 0, st>>>(src, ld, row0, col0, rv, cv, colscale, dst, rp, cp);
+  else if (fmt == 0)
+    pack_image_kernel<0><<<g, 256, 0, st>>>(src, ld, row0, col0, rv, cv, colscale, dst, rp, cp);
   else
-    pack_image_kernel<false><<<ceil_div(rp * cp, 256), 256, 0, st>>>(src, ld, row0, col0, rv, cv, colscale, dst, rp, cp);
+    pack_image_kernel<2><<<g, 256, 0, st>>>(src, ld, row0, col0, rv, cv, colscale, dst, rp, cp);
+}
+void pack_bias_col(int fmt, const float *bias, int row0, int rv, uint8_t *dst, int cp, int col, cudaStream_t st) {
+  const int g = ceil_div(rv, 256);
+  if (fmt == 1)
+    pack_bias_col_kernel<1><<<g, 256, 0, st>>>(bias, row0, rv, dst, cp, col);
+  else if (fmt == 0)
+    pack_bias_col_kernel<0><<<g, 256, 0, st>>>(bias, row0, rv, dst, cp, col);
+  else
+    pack_bias_col_kernel<2><<<g, 256, 0, st>>>(bias, row0, rv, dst, cp, col);
 }
 
 constexpr size_t kApplySmem = (size_t)kTile144 + kW144 + kApplyStage;
@@ -376,10 +407,12 @@ int forward_tc_t(const void *packed_fp32, const void *packed_tc, const float *x,
   const uint8_t *tcw = base + (F16 ? L.img_bytes : 0);
   const float *wvp = reinterpret_cast<const float *>(base + L.wvp);
   const float *bvp = reinterpret_cast<const float *>(base + L.bvp);
-  const float *bqp = reinterpret_cast<const float *>(base + L.bqp);
-  const float *bkp = reinterpret_cast<const float *>(base + L.bkp);
+  const float *wqaT = reinterpret_cast<const float *>(base + L.wqaT);
+  const float *wkaT = reinterpret_cast<const float *>(base + L.wkaT);
+  const uint8_t *tcw_lo = base + L.lo;   // bf16 lo terms of the W1 / W2 chunk images
   uint8_t *ws = static_cast<uint8_t *>(ws_tc);
   float *gram = reinterpret_cast<float *>(ws + W.gram_part);
+  float *spart = reinterpret_cast<float *>(ws + W.spart);
   float *beff = reinterpret_cast<float *>(ws + W.beff);
   uint8_t *weff = ws + W.weff;
   uint8_t *vn = ws + W.vn;
@@ -389,6 +422,7 @@ int forward_tc_t(const void *packed_fp32, const void *packed_tc, const float *x,
     if (!set_max_smem(tc_front1_kernel<F16, false>, kFront1Smem, "tc_front1_kernel") ||
         !set_max_smem(tc_front1_kernel<F16, true>, kFront1Smem, "tc_front1_kernel") ||
         !set_max_smem(tc_apply_kernel<F16>, kApplySmem, "tc_apply_kernel") ||
+        !set_max_smem(gram_project_kernel, sizeof(GpSmem), "gram_project_kernel") ||
         !set_max_smem(tc_back_kernel<F16, false>, kBackSmem, "tc_back_kernel") ||
         !set_max_smem(tc_back_kernel<F16, true>, kBackSmem, "tc_back_kernel"))
       return OTP_ERR_CUDA;
@@ -397,16 +431,16 @@ int forward_tc_t(const void *packed_fp32, const void *packed_tc, const float *x,
     LaunchScope ls(K_TC_FRONT, st);
     if (stride == 1)
       tc_front1_kernel<F16, false><<<dim3(W.nchunk, b), kFrThreads, kFront1Smem, st>>>(
-          P, tcw, bqp, bkp, x, gram, vn, t, W.tout, W.tiles, W.tiles_per_chunk, W.nchunk, 1.0f / sqrtf((float)kHS),
-          g_trace_on);
+          P, x, gram, vn, t, W.tout, W.tiles, W.tiles_per_chunk, W.nchunk, g_trace_on);
     else
       tc_front1_kernel<F16, true><<<dim3(W.nchunk, b), kFrThreads, kFront1Smem, st>>>(
-          P, tcw, bqp, bkp, x, gram, vn, t, W.tout, W.tiles, W.tiles_per_chunk, W.nchunk, 1.0f / sqrtf((float)kHS),
-          g_trace_on);
+          P, x, gram, vn, t, W.tout, W.tiles, W.tiles_per_chunk, W.nchunk, g_trace_on);
   }
   {
-    LaunchScope ls(K_BLOCK_FOLD, st);
-    block_fold_kernel<kC, F16 ? 2 : 1><<<dim3(b, FoldCfg<kC>::NBLK), kFoldThreads, 0, st>>>(wvp, bvp, gram, W.nchunk,
+    // S = Wq~ G~ Wk~^T in fp32 (8 column blocks per clip), then softmax + W_eff fold
+    LaunchScope ls(K_BLOCK_FOLD, st, 2);
+    gram_project_kernel<<<dim3(kGpBlocks, b), kGpThreads, sizeof(GpSmem), st>>>(gram, W.nchunk, wqaT, wkaT, spart);
+    block_fold_kernel<kC, F16 ? 2 : 1><<<dim3(b, FoldCfg<kC>::NBLK), kFoldThreads, 0, st>>>(wvp, bvp, spart, kGramBlocks,
                                                                                            weff, beff, kKP, kKP);
   }
   {
@@ -422,9 +456,11 @@ int forward_tc_t(const void *packed_fp32, const void *packed_tc, const float *x,
     const int total = b * W.tiles;
     const int grid = min(total, num_sms());
     if (stride == 1)
-      tc_back_kernel<F16, false><<<grid, kBackThreads, kBackSmem, st>>>(P, tcw, x, obuf, y, b, t, W.tout, W.tiles, g_trace_on);
+      tc_back_kernel<F16, false><<<grid, kBackThreads, kBackSmem, st>>>(P, tcw, tcw_lo, x, obuf, y, b, t, W.tout, W.tiles,
+                                                                        g_trace_on);
     else
-      tc_back_kernel<F16, true><<<grid, kBackThreads, kBackSmem, st>>>(P, tcw, x, obuf, y, b, t, W.tout, W.tiles, g_trace_on);
+      tc_back_kernel<F16, true><<<grid, kBackThreads, kBackSmem, st>>>(P, tcw, tcw_lo, x, obuf, y, b, t, W.tout, W.tiles,
+                                                                       g_trace_on);
   }
   return check_launch("block_forward_tc");
 }
@@ -450,17 +486,16 @@ int block_tc_pack(const otp_block_params *p, int c, void *packed_tc, cudaStream_
   if (c != kC) return OTP_OK;
   constexpr TcPack L = tc_pack_layout();
   uint8_t *base = static_cast<uint8_t *>(packed_tc);
-  LaunchScope ls(K_PACK, st, 61);
-  for (int f = 0; f < 2; ++f) {
-    uint8_t *d = base + f * L.img_bytes;
-    // LN_q / LN_k / LN2 affine folded in: W' = W diag(g), b' = b + W beta (fp32 vectors below)
-    pack_image(f, p->q_w, kC, 0, 0, kC, kC, p->q_norm_w, d + L.wq, kKP, kKP, st);
-    pack_image(f, p->k_w, kC, 0, 0, kC, kC, p->k_norm_w, d + L.wk, kKP, kKP, st);
-    pack_image(f, p->proj_w, kC, 0, 0, kC, kC, nullptr, d + L.wp, kKP, kKP, st);
+  LaunchScope ls(K_PACK, st, 107);
+  for (int f = 0; f < 3; ++f) {   // 0: bf16 (hi), 1: fp16, 2: bf16 lo terms (W1 / W2 only)
+    uint8_t *d = f < 2 ? base + f * L.img_bytes : base + L.lo - L.w1;
+    const int fmt = f == 1 ? 1 : (f == 2 ? 2 : 0);
+    // LN2 affine folded in: W1' = W1 diag(g2), b1' = b1 + W1 beta2 (fp32 vector below)
+    if (f < 2) pack_image(fmt, p->proj_w, kC, 0, 0, kC, kC, nullptr, d + L.wp, kKP, kKP, st);
     for (int j = 0; j < kNChunk; ++j) {
       const int hv = min(kNH, 4 * kC - j * kNH);
-      pack_image(f, p->mlp0_w, kC, j * kNH, 0, hv, kC, p->ln2_w, d + L.w1 + (size_t)j * kW1c, kNH, kKP, st);
-      pack_image(f, p->mlp3_w, 4 * kC, 0, j * kNH, kC, hv, nullptr, d + L.w2 + (size_t)j * kW2c, kKP, kNH, st);
+      pack_image(fmt, p->mlp0_w, kC, j * kNH, 0, hv, kC, p->ln2_w, d + L.w1 + (size_t)j * kW1c, kNH, kKP, st);
+      pack_image(fmt, p->mlp3_w, 4 * kC, 0, j * kNH, kC, hv, nullptr, d + L.w2 + (size_t)j * kW2c, kKP, kNH, st);
     }
   }
   scale_cols_kernel<<<ceil_div(kC * kC, 256), 256, 0, st>>>(p->v_w, p->v_norm_w, reinterpret_cast<float *>(base + L.wvp),
@@ -470,19 +505,19 @@ int block_tc_pack(const otp_block_params *p, int c, void *packed_tc, cudaStream_
   fold_bias_kernel<<<1, 256, 0, st>>>(p->k_w, p->k_b, p->k_norm_b, reinterpret_cast<float *>(base + L.bkp), kC, kC, kKP);
   fold_bias_kernel<<<ceil_div(kHidPad, 256), 256, 0, st>>>(p->mlp0_w, p->mlp0_b, p->ln2_b,
                                                            reinterpret_cast<float *>(base + L.b1p), 4 * kC, kC, kHidPad);
-  // biases folded into operand column 136 (tc_back): b_p into Wp, b_1 + W_1 beta_2 into the W1 chunks
+  // augmented, transposed, LayerNorm-folded q / k projections in fp32 (1/sqrt(hs) folded into Wq~)
+  pack_aug_T_kernel<<<ceil_div(kKP * kKP, 256), 256, 0, st>>>(p->q_w, p->q_norm_w, reinterpret_cast<const float *>(base + L.bqp),
+                                                              1.0f / sqrtf((float)kHS), reinterpret_cast<float *>(base + L.wqaT));
+  pack_aug_T_kernel<<<ceil_div(kKP * kKP, 256), 256, 0, st>>>(p->k_w, p->k_norm_w, reinterpret_cast<const float *>(base + L.bkp),
+                                                              1.0f, reinterpret_cast<float *>(base + L.wkaT));
+  // biases folded into operand column 136 (tc_back): b_p into Wp, b_1 + W_1 beta_2 into the W1 chunks (hi images;
+  // the lo images carry the bias's bf16 remainder in bfloat16 mode)
   const float *b1f = reinterpret_cast<const float *>(base + L.b1p);
-  for (int f = 0; f < 2; ++f) {
-    uint8_t *d = base + f * L.img_bytes;
-    if (f) {
-      pack_bias_col_kernel<true><<<1, 256, 0, st>>>(p->proj_b, 0, kC, d + L.wp, kKP, kC);
-      for (int j = 0; j < kNChunk; ++j)
-        pack_bias_col_kernel<true><<<1, 64, 0, st>>>(b1f, j * kNH, kNH, d + L.w1 + (size_t)j * kW1c, kKP, kC);
-    } else {
-      pack_bias_col_kernel<false><<<1, 256, 0, st>>>(p->proj_b, 0, kC, d + L.wp, kKP, kC);
-      for (int j = 0; j < kNChunk; ++j)
-        pack_bias_col_kernel<false><<<1, 64, 0, st>>>(b1f, j * kNH, kNH, d + L.w1 + (size_t)j * kW1c, kKP, kC);
-    }
+  for (int f = 0; f < 3; ++f) {
+    uint8_t *d = f < 2 ? base + f * L.img_bytes : base + L.lo - L.w1;
+    const int fmt = f == 1 ? 1 : (f == 2 ? 2 : 0);
+    if (f < 2) pack_bias_col(fmt, p->proj_b, 0, kC, d + L.wp, kKP, kC, st);
+    for (int j = 0; j < kNChunk; ++j) pack_bias_col(fmt, b1f, j * kNH, kNH, d + L.w1 + (size_t)j * kW1c, kKP, kC, st);
   }
   return check_launch("block_tc_pack");
 }

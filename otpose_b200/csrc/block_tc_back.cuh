@@ -128,7 +128,8 @@ __device__ __forceinline__ size_t back_chunk_offset(const TcPack &L, int q) {
 
 template <bool F16, bool S2>
 __global__ void __launch_bounds__(kBackThreads, 1)
-tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__restrict__ x,
+tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const uint8_t *__restrict__ tcw_lo,
+               const float *__restrict__ x,
                const unsigned short *__restrict__ obuf, float *__restrict__ y, int B, int T, int Tout, int tiles,
                int trace) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -141,6 +142,10 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__rest
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr TcPack L = tc_pack_layout();
+  // bfloat16 mode: every W1 / W2 chunk is streamed and multiplied twice (hi term, then the lo remainder
+  // into the same accumulator) -- a rounded weight perturbs every token coherently, see block_tc_front.cuh
+  constexpr bool kSplit = !F16;
+  constexpr int kPasses = kSplit ? 2 : 1;
   const int total = B * tiles;
   const int ntile = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
 
@@ -188,15 +193,19 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__rest
     if (ntile > 0) tma_elect(wpb, tcw + L.wp, kW144, &bars.wpfull);
     const int nload = kBackLoads * ntile;
     int q = 0, slot = 0;
-    uint32_t round = 0;   // gq / kBackSlots
+    uint32_t round = 0;   // loads / kBackSlots
     for (int gq = 0; gq < nload; ++gq) {
-      if (round > 0) mbar_wait(&bars.wempty[slot], (round - 1) & 1);
-      tma_elect(ring + slot * kW1c, tcw + back_chunk_offset(L, q), kW1c, &bars.wfull[slot]);
-      if (++q == kBackLoads) q = 0;
-      if (++slot == kBackSlots) {
-        slot = 0;
-        ++round;
+      const size_t off = back_chunk_offset(L, q);
+#pragma unroll
+      for (int pass = 0; pass < kPasses; ++pass) {
+        if (round > 0) mbar_wait(&bars.wempty[slot], (round - 1) & 1);
+        tma_elect(ring + slot * kW1c, pass ? tcw_lo + (off - L.w1) : tcw + off, kW1c, &bars.wfull[slot]);
+        if (++slot == kBackSlots) {
+          slot = 0;
+          ++round;
+        }
       }
+      if (++q == kBackLoads) q = 0;
     }
   } else if (warp == kBackEpi / 32) {
     // =============================================================== MMA ISSUER
@@ -236,12 +245,15 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__rest
       const int c0 = kNChunk * it;
       const uint32_t aa = ab + (it & 1) * kTile144;
       auto mma1 = [&](int c) {   // D_h[c%3] = [LN2(u) | 1] . [W1_j | b1_j]^T
-        const uint32_t w1 = next_chunk();
 #pragma unroll
-        for (int s = 0; s < kKP / 16; ++s)
-          umma_elect(t_h + (c % kBackTH) * kNH, make_desc(aa + s * 2 * kCS, kCS, kRS144),
-                     make_desc(w1 + s * 2 * kCS, kCS, kRS144), idescH, s > 0);
-        release_chunk();
+        for (int pass = 0; pass < kPasses; ++pass) {
+          const uint32_t w1 = next_chunk();
+#pragma unroll
+          for (int s = 0; s < kKP / 16; ++s)
+            umma_elect(t_h + (c % kBackTH) * kNH, make_desc(aa + s * 2 * kCS, kCS, kRS144),
+                       make_desc(w1 + s * 2 * kCS, kCS, kRS144), idescH, (pass > 0 || s > 0));
+          release_chunk();
+        }
         commit_elect(&bars.thfull[c % kBackTH]);
       };
       tr(0);
@@ -258,14 +270,17 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__rest
         mbar_wait(&bars.hbfull[c % kBackHB], (c / kBackHB) & 1);
         tr(10 + j);
         tc_fence_after();
-        const uint32_t w2 = next_chunk();
-        tr(30 + j);
         const uint32_t hh = hb + (c % kBackHB) * kHTile;
 #pragma unroll
-        for (int s = 0; s < kNH / 16; ++s)
-          umma_elect(t_y, make_desc(hh + s * 2 * kCS, kCS, kRSH), make_desc(w2 + s * 2 * kCS, kCS, kRSH), idesc144,
-                     (j > 0 || s > 0));
-        release_chunk();
+        for (int pass = 0; pass < kPasses; ++pass) {
+          const uint32_t w2 = next_chunk();
+          if (pass == 0) tr(30 + j);
+#pragma unroll
+          for (int s = 0; s < kNH / 16; ++s)
+            umma_elect(t_y, make_desc(hh + s * 2 * kCS, kCS, kRSH), make_desc(w2 + s * 2 * kCS, kCS, kRSH), idesc144,
+                       (j > 0 || s > 0 || pass > 0));
+          release_chunk();
+        }
         commit_elect(&bars.hbfree[c % kBackHB]);
         if (j == kNChunk - 1) commit_elect(&bars.yfull);
         if (j + 3 < kNChunk) mma1(c + 3);   // t_h[c%3] was drained by GELU(chunk c) before hbfull[c%3]

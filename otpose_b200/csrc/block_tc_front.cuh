@@ -1,37 +1,51 @@
-// tc_front: LN1 -> {dw_q, dw_k, dw_v} -> {LN_q, LN_k, LN_v} -> q / k projections -> per-CTA partial
-// channel Gram, of one TransformerBlock (model/blocks.py:264-268, 400-440), stride-1 stem blocks and
-// (template S2) stride-2 branch blocks.  Included by block_tc.cu inside its anonymous namespace.
+// tc_front: LN1 -> {dw_q, dw_k, dw_v} -> {LN_q, LN_k, LN_v} -> per-CTA partial AUGMENTED channel Gram of
+// one TransformerBlock (model/blocks.py:264-268, 400-440), stride-1 stem blocks and (template S2)
+// stride-2 branch blocks.  Included by block_tc.cu inside its anonymous namespace.
+//
+// "Gram first": the reference forms q = W_q a + b_q, k = W_k c + b_k per token (a = LN_q(dw_q(LN1 x)),
+// c = LN_k(dw_k(LN1 x))) and reduces S_h = sum_t q_h k_h^T over ALL tokens of the clip.  Both maps are
+// linear in the token, so with a~ = [a; 1], c~ = [c; 1]
+//
+//     S_h = [W_q | b_q]_h  ( sum_t a~_t c~_t^T )  [W_k | b_k]_h^T  =  Wq~_h  G~  Wk~_h^T ,
+//
+// and only the 137 x 137 Gram G~ of the NORMALISED depthwise outputs has to be accumulated over the
+// tokens; the two projections are applied once per clip, in fp32, by the fold kernels (block_fold.cuh,
+// gram_project_kernel below).  This removes two of the three per-token GEMMs of this pass, their
+// TMEM -> bias -> 16-bit write-back epilogues and both resident weight images, and -- the reason it was
+// done -- W_q / W_k are never rounded to 16 bits: a rounded weight is the same perturbation for every
+// token, so its error adds up coherently over the 6912-token reduction and is then amplified by the
+// softmax (scripts/emulate_operand_rounding.py: 1.1e-2 of the 1.3e-2 bfloat16 feature error), whereas
+// the rounding of a_t / c_t is independent per token and averages out.
 //
 // One warp-specialised CTA per (clip, token chunk), 448 threads:
 //   warps 0-11  COMPUTE: thread (q4, lane, third) owns token 32*q4 + lane and 48 channels.  The
 //               token's x values are loaded straight into registers one tile ahead (no fp32 staging
 //               tile); LN1(x) is exchanged between neighbouring tokens through a 16-bit (IEEE half)
-//               shared tile, which is what frees the shared memory to keep BOTH Wq and Wk resident.
-//   warp 12     MMA ISSUER (converged warp, elect-predicated tcgen05.mma): q projection as soon as
-//               the q operand tile is staged (it runs under the k pass), k projection under the v
-//               pass, the channel Gram (MN-major views of the q / k tiles) under the next tile's LN1.
+//               shared tile.  a_t / c_t go into 16-bit [token][channel] operand tiles (channel 136 = the
+//               ones column), double buffered; vn (the v branch) goes to global memory for tc_apply.
+//   warp 12     MMA ISSUER (converged warp, elect-predicated tcgen05.mma): G~ += a~^T c~ over the tile's
+//               128 tokens -- MN-major views of the two tiles, two M = 128 row blocks (channels 0..127 and
+//               16..143), N = 144, accumulated in TMEM over the CTA's whole token chunk.  Runs under the
+//               next tile's LayerNorm / depthwise work.
 //   warp 13     HALO: LN1 of the two tokens next to the tile (t0-1, t0+128), one tile ahead.
 constexpr int kFrComp = 384;
 constexpr int kFrThreads = kFrComp + 64;
 constexpr uint32_t kHsRow = kC * 2;           // 272-byte row of 136 halves: 16-byte accesses of
                                               // consecutive lanes fall into distinct bank groups
+constexpr int kGramLd = kKP;                  // row stride (floats) of a partial G~ in global memory
+constexpr int kGramRows = kC + 1;             // 137: channels + the ones row
 struct Front1Vec {
   float ln1w[kC], ln1b[kC];
   float4 dw[3][kC];          // depthwise taps of q, k, v
-  float bq[kKP], bk[kKP];    // folded biases
   float part[2][4][3][kTM];  // [parity of the pass][mean | M2 or sum | sumsq (| odd input: mean | M2)][third][token]
 };
 struct Front1Bars {
-  uint64_t wfull;            // TMA arrival of Wq | Wk
-  uint64_t qfull, kfull;     // compute -> MMA: operand tile staged (12 warp arrivals)
-  uint64_t gfull;            // compute -> MMA: q / k written back for the Gram (12 warp arrivals)
-  uint64_t qdone, kdone;     // projection accumulators ready
-  uint64_t gdone;            // Gram UMMAs done: aq / ak reusable
+  uint64_t abfull[2];        // compute -> MMA: a~ and c~ tiles of buffer s staged (12 warp arrivals)
+  uint64_t gdone[2];         // Gram UMMAs reading buffer s done: buffer reusable
   uint64_t halo_full[2];     // halo rows of tile n staged in halo[n & 1]
   uint64_t adone;            // compute warps are done reading the LN1 tile / halo rows (12 warp arrivals)
 };
-constexpr size_t kFront1Smem =
-    (size_t)kTM * kHsRow + 4 * kHsRow + 2 * kTile144 + 2 * kW144 + sizeof(Front1Vec);
+constexpr size_t kFront1Smem = (size_t)kTM * kHsRow + 4 * kHsRow + 4 * kTile144 + sizeof(Front1Vec);
 static_assert(kFront1Smem + 1024 <= 227 * 1024, "tc_front1 shared memory");
 
 __device__ __forceinline__ void fr_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kFrComp) : "memory"); }
@@ -50,25 +64,21 @@ __device__ __forceinline__ void unpack8(const uint4 &p, float (&f)[8]) {
 // input goes to the shared tile (row j = input 2j+1: its own right tap and token j+1's left tap), so
 // the tile is the same size as for stride 1; only a left halo row (input 2*t0-1) is needed.  The two
 // input tokens are loaded at the start of the tile (no register room to prefetch them a tile ahead).
+// 14 warps: the busiest scheduler partition holds 4 of them, i.e. 16384 / 4 / 32 = 128 registers per thread
 template <bool F16, bool S2>
 __global__ void __launch_bounds__(kFrThreads, 1)
-tc_front1_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__restrict__ bqp,
-                 const float *__restrict__ bkp, const float *__restrict__ x, float *__restrict__ gram_part,
+tc_front1_kernel(BlockPack P, const float *__restrict__ x, float *__restrict__ gram_part,
                  uint8_t *__restrict__ vn_img, int T, int Tout, int tiles, int tiles_per_chunk, int nchunk,
-                 float qscale, int trace) {
+                 int trace) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t *aq = smem;
-  uint8_t *ak = aq + kTile144;
-  uint8_t *wq = ak + kTile144;
-  uint8_t *wk = wq + kW144;
-  uint8_t *hs = wk + kW144;                    // [128][136] halves: LN1(x) of the tile's tokens
+  uint8_t *ab = smem;                          // [2 buffers][a~ tile | c~ tile], [token][channel] 16-bit
+  uint8_t *hs = ab + 4 * kTile144;             // [128][136] halves: LN1(x) of the tile's tokens
   uint8_t *halo = hs + kTM * kHsRow;           // [2][2][136] halves: LN1(x) of tokens t0-1 / t0+128
   Front1Vec *V = reinterpret_cast<Front1Vec *>(halo + 4 * kHsRow);
   __shared__ Front1Bars bars;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y, chunk = blockIdx.x;
-  constexpr TcPack L = tc_pack_layout();
   const int tile_begin = chunk * tiles_per_chunk;
   const int tile_end = min(tiles, tile_begin + tiles_per_chunk);
 
@@ -79,21 +89,14 @@ tc_front1_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__re
     V->dw[1][c] = make_float4(P.dwk[3 * c], P.dwk[3 * c + 1], P.dwk[3 * c + 2], 0.f);
     V->dw[2][c] = make_float4(P.dwv[3 * c], P.dwv[3 * c + 1], P.dwv[3 * c + 2], 0.f);
   }
-  for (int c = threadIdx.x; c < kKP; c += kFrThreads) {
-    V->bq[c] = bqp[c];
-    V->bk[c] = bkp[c];
-  }
   if (threadIdx.x == 0) {
-    mbar_init(&bars.wfull, 1);
-    mbar_init(&bars.qfull, kFrComp / 32);
-    mbar_init(&bars.kfull, kFrComp / 32);
-    mbar_init(&bars.gfull, kFrComp / 32);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars.abfull[i], kFrComp / 32);
+      mbar_init(&bars.gdone[i], 1);
+      mbar_init(&bars.halo_full[i], 1);
+    }
     mbar_init(&bars.adone, kFrComp / 32);
-    mbar_init(&bars.qdone, 1);
-    mbar_init(&bars.kdone, 1);
-    mbar_init(&bars.gdone, 1);
-    mbar_init(&bars.halo_full[0], 1);
-    mbar_init(&bars.halo_full[1], 1);
     fence_mbar_init();
   }
   if (warp == kFrComp / 32) tmem_alloc(&tmem_slot, 512);
@@ -101,50 +104,28 @@ tc_front1_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__re
   __syncthreads();
   tc_fence_after();
   const uint32_t tm = tmem_slot;
-  const uint32_t t_q = tm, t_k = tm + 144, t_g0 = tm + 288, t_g1 = tm + 368;
+  const uint32_t t_g0 = tm, t_g1 = tm + kKP;   // rows = a~ channels 0..127 / 16..143, columns = c~ channels
   constexpr uint32_t kFmt = F16 ? 0u : 1u;
   const float *xb = x + (size_t)b * kC * T;
 
   if (warp == kFrComp / 32) {
     // =============================================================== MMA ISSUER
-    const uint32_t idesc_qk = make_idesc_16(kKP, false, false, kFmt);
-    const uint32_t idesc_gram = make_idesc_16(80, true, true, kFmt);
-    const uint32_t a_q = smem_u32(aq), a_k = smem_u32(ak), w_q = smem_u32(wq), w_k = smem_u32(wk);
-    static_assert(tc_pack_layout().wk == tc_pack_layout().wq + kW144, "Wq | Wk are one contiguous image");
-    if (tile_begin < tile_end) {
-      tma_elect(wq, tcw + L.wq, 2 * kW144, &bars.wfull);
-      mbar_wait(&bars.wfull, 0);
-    }
+    const uint32_t idesc_gram = make_idesc_16(kKP, true, true, kFmt);
+    const uint32_t ab0 = smem_u32(ab);
     uint32_t n = 0;
     for (int tile = tile_begin; tile < tile_end; ++tile, ++n) {
-      mbar_wait(&bars.qfull, n & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int s = 0; s < kKP / 16; ++s)
-        umma_elect(t_q, make_desc(a_q + s * 2 * kCS, kCS, kRS144), make_desc(w_q + s * 2 * kCS, kCS, kRS144), idesc_qk,
-                   s > 0);
-      commit_elect(&bars.qdone);
-      mbar_wait(&bars.kfull, n & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int s = 0; s < kKP / 16; ++s)
-        umma_elect(t_k, make_desc(a_k + s * 2 * kCS, kCS, kRS144), make_desc(w_k + s * 2 * kCS, kCS, kRS144), idesc_qk,
-                   s > 0);
-      commit_elect(&bars.kdone);
-      // ---- channel Gram over this tile's tokens: MN-major views of the written-back q / k tiles ----
-      mbar_wait(&bars.gfull, n & 1);
+      const uint32_t a_s = ab0 + (n & 1) * 2 * kTile144, c_s = a_s + kTile144;
+      mbar_wait(&bars.abfull[n & 1], (n >> 1) & 1);
       tc_fence_after();
 #pragma unroll
       for (int s = 0; s < kTM / 16; ++s) {
-        const uint32_t ko = s * 2 * kRS144;
-        // head 0: rows = q channels 0..127, cols = k channels 0..79
-        umma_elect(t_g0, make_desc(a_q + ko, kRS144, kCS), make_desc(a_k + ko, kRS144, kCS), idesc_gram,
+        const uint32_t ko = s * 2 * kRS144;   // 16 tokens = two 8-row groups
+        umma_elect(t_g0, make_desc(a_s + ko, kRS144, kCS), make_desc(c_s + ko, kRS144, kCS), idesc_gram,
                    !(n == 0 && s == 0));
-        // head 1: rows = q channels 8..135, cols = k channels 64..143
-        umma_elect(t_g1, make_desc(a_q + ko + kCS, kRS144, kCS), make_desc(a_k + ko + 8 * kCS, kRS144, kCS), idesc_gram,
+        umma_elect(t_g1, make_desc(a_s + ko + 2 * kCS, kRS144, kCS), make_desc(c_s + ko, kRS144, kCS), idesc_gram,
                    !(n == 0 && s == 0));
       }
-      commit_elect(&bars.gdone);
+      commit_elect(&bars.gdone[n & 1]);
     }
   } else if (warp == kFrComp / 32 + 1) {
     // =============================================================== HALO
@@ -218,6 +199,7 @@ tc_front1_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__re
       const bool live = tok < nvalid;                             // output token (and its even input) exists
       const bool live_o = S2 && 2 * (t0 + tok) + 1 < T;           // its odd input exists
       uint8_t *vn_tile = vn_img + ((size_t)b * tiles + tile) * kTile144;
+      uint8_t *a_tile = ab + (n & 1) * 2 * kTile144, *c_tile = a_tile + kTile144;
       tr(0);
       if (S2) load_x(tile);
       // ---- LN1 over the token's 136 channels: per-thread (mean, M2), parallel-variance combine ----
@@ -313,8 +295,8 @@ tc_front1_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__re
       const uint8_t *rrow = S2 ? hrow   // stride 2: the right tap is this token's own odd input
                                : (tok == kTM - 1 ? halo + ((n & 1) * 2 + 1) * kHsRow + c_lo * 2 : hrow + kHsRow);
       // ---- q, k, v in turn: depthwise conv (registers) -> statistics -> (d - mean) * rstd -> operand tile ----
-#pragma unroll 1
-      for (int m = 0; m < 3; ++m) {
+      auto pass = [&](auto mc) {
+        constexpr int m = decltype(mc)::value;
         float d[48];
         float s = 0.f, ss = 0.f;
 #pragma unroll
@@ -353,86 +335,54 @@ tc_front1_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__re
         const float rstd = 1.0f / sqrtf(var + 1e-5f);
         const float nmr = -mean * rstd;   // (d - mean) * rstd as one FMA
         pp ^= 1;
-        // the previous tile's Gram UMMAs still read aq / ak: wait before overwriting them
-        if (m == 0 && n > 0) mbar_wait(&bars.gdone, (n - 1) & 1);
+        // the Gram UMMAs of tile n-2 still read this buffer's a~ / c~ tiles: wait before overwriting them
+        if (m == 0 && n >= 2) mbar_wait(&bars.gdone[n & 1], ((n >> 1) - 1) & 1);
         tr(30 + m);
-        uint8_t *dst = (m == 0 ? aq : (m == 1 ? ak : vn_tile)) + cm_offset(tok, c_lo, kRS144, kCS);
+        uint8_t *dst = (m == 0 ? a_tile : (m == 1 ? c_tile : vn_tile)) + cm_offset(tok, c_lo, kRS144, kCS);
 #pragma unroll
         for (int g = 0; g < 6; ++g) {
           float o8[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o8[e] = (g * 8 + e < nq) ? fmaf(d[g * 8 + e], rstd, nmr) : 0.f;
+          for (int e = 0; e < 8; ++e)   // rows of tokens past the sequence end are zero: they must not reach G~
+            o8[e] = (g * 8 + e < nq && (m == 2 || live)) ? fmaf(d[g * 8 + e], rstd, nmr) : 0.f;
+          // channel 136 of a~ / c~ = 1 for the tile's real tokens: row / column 136 of G~ carry sum_t c_t,
+          // sum_t a_t and the token count, which is how b_q / b_k enter S (gram_project_kernel)
+          if (m < 2 && g == 5 && third == 2) o8[0] = live ? 1.f : 0.f;
           *reinterpret_cast<uint4 *>(dst + g * kCS) = pack16x8<F16>(o8);
         }
-        if (m < 2) {
-          fence_async_smem();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(m == 0 ? &bars.qfull : &bars.kfull);
-        }
         tr(40 + m);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars.adone);
-      // next tile's x: issued after the proxy fences of the q and k passes (fence.proxy.async waits for the
-      // thread's pending loads), in flight during the epilogue
-      if (!S2 && tile + 1 < tile_end) load_x(tile + 1);
-      // ---- epilogue: + bias, * 1/sqrt(hs) for q, 16 bit, back into aq / ak as [token][channel] ----
-      {
-        const uint32_t off = cm_offset(tok, c_lo, kRS144, kCS);
-        float v[48];
-        tr(50);
-        mbar_wait(&bars.qdone, n & 1);
-        tc_fence_after();
-        tr(51);
-        tmem_ld48(tcol(t_q, q4, c_lo), v);
-#pragma unroll
-        for (int g = 0; g < 6; ++g) {
-          float o8[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o8[e] = live ? (v[g * 8 + e] + V->bq[c_lo + g * 8 + e]) * qscale : 0.f;
-          *reinterpret_cast<uint4 *>(aq + off + g * kCS) = pack16x8<F16>(o8);
-        }
-        tr(52);
-        mbar_wait(&bars.kdone, n & 1);
-        tc_fence_after();
-        tr(53);
-        tmem_ld48(tcol(t_k, q4, c_lo), v);
-#pragma unroll
-        for (int g = 0; g < 6; ++g) {
-          float o8[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o8[e] = live ? v[g * 8 + e] + V->bk[c_lo + g * 8 + e] : 0.f;
-          *reinterpret_cast<uint4 *>(ak + off + g * kCS) = pack16x8<F16>(o8);
-        }
-      }
-      tr(54);
+      };
+      pass(std::integral_constant<int, 0>{});
+      pass(std::integral_constant<int, 1>{});
       fence_async_smem();
-      tr(55);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars.gfull);
+      if (lane == 0) mbar_arrive(&bars.abfull[n & 1]);
+      // next tile's x: issued behind the tile's only proxy fence (fence.proxy.async waits for the thread's
+      // pending loads), in flight during the v pass
+      if (!S2 && tile + 1 < tile_end) load_x(tile + 1);
+      pass(std::integral_constant<int, 2>{});
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.adone);
     }
-    // ---- flush the partial Gram: TMEM lane == q channel (row), column == k channel ----
+    // ---- flush the partial G~: TMEM lane == a~ channel (row), column == c~ channel ----
     if (n > 0) {
-      mbar_wait(&bars.gdone, (n - 1) & 1);
+      mbar_wait(&bars.gdone[(n - 1) & 1], ((n - 1) >> 1) & 1);   // commits complete in order: every tile is in
       tc_fence_after();
-      if (third < 2) {
-        float *gp = gram_part + (size_t)(b * nchunk + chunk) * kC * kHS;
-        const int row_ch = third ? 8 + tok : tok;          // q channel of this lane
-        const bool row_ok = third ? (row_ch >= kHS && row_ch < kC) : (row_ch < kHS);
-        const int col0 = third ? 4 : 0;                     // first useful column
-        const uint32_t tg = third ? t_g1 : t_g0;
+      float *gp = gram_part + (size_t)(b * nchunk + chunk) * kKP * kGramLd;
 #pragma unroll 1
-        for (int g = 0; g < 10; ++g) {
+      for (int blk = 0; blk < 2; ++blk) {
+        if (blk == 1 && q4 != 3) break;                       // row block 1 only contributes channels 128..136
+        const int row_ch = blk ? 16 + tok : tok;
+        const bool row_ok = blk ? (row_ch >= kTM && row_ch < kGramRows) : true;
+#pragma unroll 1
+        for (int g = 0; g < 6; ++g) {
           float v[8];
-          tmem_ld8(tcol(tg, q4, g * 8), v);
+          tmem_ld8(tcol(blk ? t_g1 : t_g0, q4, c_lo + g * 8), v);
           if (row_ok) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int j = g * 8 + e - col0;
-              if (j >= 0 && j < kHS) gp[(size_t)row_ch * kHS + j] = v[e];
-            }
+            float4 *dst = reinterpret_cast<float4 *>(gp + (size_t)row_ch * kGramLd + c_lo + g * 8);
+            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
           }
         }
       }
@@ -441,4 +391,118 @@ tc_front1_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const float *__re
   tc_fence_before();
   __syncthreads();
   if (warp == kFrComp / 32) tmem_dealloc(tm, 512);
+}
+
+// ------------------------------------------------------------------ gram_project (fold, part 1)
+// S = Wq~ G~ Wk~^T per head, split over 8 column blocks J of G~ so that 8 * B CTAs share the work and every
+// CTA reduces only its own 18 columns of the per-chunk partial Grams (fixed order: deterministic):
+//     G_J   = sum_chunks part[chunk][:, J]                         (137 x 18)
+//     M1_J  = Wq~ G_J                                              (136 x 18)
+//     S^(J)[i][m] = sum_{j in J} M1_J[i][j] Wk~[h(i)*68 + m][j]    (136 x 68 partial of S)
+// The 8 partials are summed (again in fixed order) by block_fold_kernel, which also does the softmax and
+// the W_eff fold.  wqaT / wkaT: fp32 [144][144] TRANSPOSED augmented weights ([r][i] = Wq~[i][r], LayerNorm
+// affine and 1/sqrt(hs) folded in, row 136 = the folded bias), so consecutive threads read consecutive
+// addresses.
+constexpr int kGpCols = 18, kGpBlocks = kKP / kGpCols, kGpThreads = 2 * kKP;
+static_assert(kGpBlocks * kGpCols == kKP && kGpCols % 2 == 0 && kHS % 2 == 0, "column blocks tile the padded Gram");
+constexpr int kGpElems = (kGramRows * (kGpCols / 2) + kGpThreads - 1) / kGpThreads;   // float2 elements per thread (5)
+struct GpSmem {
+  float wq[kGramRows][kKP];        // Wq~^T rows 0..136 (cp.async, lands under the chunk reduction)
+  float wk[kGpCols][kKP];          // Wk~^T rows j0 .. j0+17
+  float G[kGramRows][kGpCols];
+  float M1[kC][kGpCols + 1];       // odd row stride: conflict-free row-per-thread stores
+};
+__global__ void __launch_bounds__(kGpThreads)
+gram_project_kernel(const float *__restrict__ gram_part, int nchunk, const float *__restrict__ wqaT,
+                    const float *__restrict__ wkaT, float *__restrict__ spart) {
+  extern __shared__ __align__(16) uint8_t gp_smem[];
+  GpSmem &sm = *reinterpret_cast<GpSmem *>(gp_smem);
+  const int b = blockIdx.y, J = blockIdx.x, j0 = J * kGpCols;
+  // weights: 16-byte async copies (both arrays are contiguous row ranges of the packed matrices)
+  for (int o = threadIdx.x; o < kGramRows * kKP / 4; o += kGpThreads)
+    cp_async16(&sm.wq[0][0] + 4 * o, wqaT + 4 * o);
+  for (int o = threadIdx.x; o < kGpCols * kKP / 4; o += kGpThreads)
+    cp_async16(&sm.wk[0][0] + 4 * o, wkaT + (size_t)j0 * kKP + 4 * o);
+  cp_async_commit();
+  // G_J = fixed-order sum of the chunk partials; every load of a chunk is issued before the first add
+  const float *gp = gram_part + (size_t)b * nchunk * kKP * kGramLd + j0;
+  {
+    float2 acc[kGpElems];
+    size_t off[kGpElems];
+#pragma unroll
+    for (int k = 0; k < kGpElems; ++k) {
+      const int e = min(threadIdx.x + k * kGpThreads, kGramRows * (kGpCols / 2) - 1);
+      off[k] = (size_t)(e / (kGpCols / 2)) * kGramLd + 2 * (e % (kGpCols / 2));
+      acc[k] = make_float2(0.f, 0.f);
+    }
+#pragma unroll 3
+    for (int ch = 0; ch < nchunk; ++ch) {
+      float2 v[kGpElems];
+#pragma unroll
+      for (int k = 0; k < kGpElems; ++k)
+        v[k] = __ldg(reinterpret_cast<const float2 *>(gp + (size_t)ch * kKP * kGramLd + off[k]));
+#pragma unroll
+      for (int k = 0; k < kGpElems; ++k) {
+        acc[k].x += v[k].x;
+        acc[k].y += v[k].y;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kGpElems; ++k) {
+      const int e = threadIdx.x + k * kGpThreads;
+      if (e < kGramRows * (kGpCols / 2)) {
+        sm.G[e / (kGpCols / 2)][2 * (e % (kGpCols / 2))] = acc[k].x;
+        sm.G[e / (kGpCols / 2)][2 * (e % (kGpCols / 2)) + 1] = acc[k].y;
+      }
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  const int half = threadIdx.x / kKP, ch = threadIdx.x % kKP;   // two threads per channel
+  if (ch < kC) {   // M1 row `ch`, columns half*9 .. half*9+8
+    constexpr int kHalfCols = kGpCols / 2;
+    float acc[kHalfCols];
+#pragma unroll
+    for (int jj = 0; jj < kHalfCols; ++jj) acc[jj] = 0.f;
+#pragma unroll 4
+    for (int r = 0; r < kGramRows; ++r) {
+      const float w = sm.wq[r][ch];
+#pragma unroll
+      for (int jj = 0; jj < kHalfCols; ++jj) acc[jj] = fmaf(w, sm.G[r][half * kHalfCols + jj], acc[jj]);
+    }
+#pragma unroll
+    for (int jj = 0; jj < kHalfCols; ++jj) sm.M1[ch][half * kHalfCols + jj] = acc[jj];
+  }
+  __syncthreads();
+  // thread = (k output channel m' = column of S within its head, half of that head's 68 rows)
+  if (ch < kC) {
+    const int h = ch / kHS, m = ch % kHS;
+    float wk[kGpCols];
+#pragma unroll
+    for (int jj = 0; jj < kGpCols; ++jj) wk[jj] = sm.wk[jj][ch];
+    float *sp = spart + ((size_t)(b * kGpBlocks + J) * kC + h * kHS) * kHS + m;
+#pragma unroll 2
+    for (int ii = half * (kHS / 2); ii < (half + 1) * (kHS / 2); ++ii) {
+      const float *mr = sm.M1[h * kHS + ii];
+      float s = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < kGpCols; ++jj) s = fmaf(mr[jj], wk[jj], s);
+      sp[(size_t)ii * kHS] = s;
+    }
+  }
+}
+
+// fp32 [144][144] transposed augmented weight: out[r][i] = w[i][r] * g[r] * scale (r, i < 136),
+// out[136][i] = bfold[i] * scale, zero elsewhere
+__global__ void pack_aug_T_kernel(const float *__restrict__ w, const float *__restrict__ g,
+                                  const float *__restrict__ bfold, float scale, float *__restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= kKP * kKP) return;
+  const int r = e / kKP, i = e % kKP;
+  float v = 0.f;
+  if (i < kC) {
+    if (r < kC) v = w[(size_t)i * kC + r] * g[r] * scale;
+    else if (r == kC) v = bfold[i] * scale;
+  }
+  out[e] = v;
 }

@@ -160,11 +160,15 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int n, bool a_mn_major, b
 
 // ---------------------------------------------------------------- packing
 // F16 = true: IEEE half operands (11-bit significand), false: bfloat16 (8-bit).
+// The half conversions SATURATE (cvt.rn.satfinite, one F2FP like the plain conversion): an activation
+// beyond +-65504 -- GELU(hidden), att @ v, post-ReLU RSB maps are unbounded with trained weights -- becomes
+// +-65504 instead of an infinity that would turn the whole clip into NaNs in the next UMMA.  NaN stays NaN.
 template <bool F16>
 __device__ __forceinline__ uint32_t pack16x2(float lo, float hi) {
   if constexpr (F16) {
-    __half2 h = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<uint32_t *>(&h);
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
   } else {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&h);
@@ -178,8 +182,9 @@ __device__ __forceinline__ uint4 pack16x8(const float *v) {
 template <bool F16>
 __device__ __forceinline__ unsigned short to16(float v) {
   if constexpr (F16) {
-    __half h = __float2half_rn(v);
-    return *reinterpret_cast<unsigned short *>(&h);
+    unsigned short h;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+    return h;
   } else {
     __nv_bfloat16 h = __float2bfloat16_rn(v);
     return *reinterpret_cast<unsigned short *>(&h);

@@ -345,11 +345,18 @@ class OTPose(nn.Module):
             if _pre is None:
                 _lib.check(lib.otp_fusion_sum_frames(_lib.dptr(rough), frames, b, j, t, total_b.data_ptr(),
                                                      squeezed.data_ptr(), st), "otp_fusion_sum_frames")
-            if getattr(self, "_rsb_precision", None) != self.precision:   # RSB convs follow the head's precision
+            # Operand format of the small convolutions behind the encoders (pyramid 1x1, RSB chains, offset /
+            # mask convs): IEEE half in BOTH 16-bit modes.  Their inputs are bounded maps (1x1-projected
+            # LayerNorm-ed features, BatchNorm + ReLU outputs; the conversions saturate), their weights are
+            # shared by every pixel, and a bfloat16-rounded weight is a token-coherent perturbation that the
+            # learned-offset sampling amplifies (scripts/emulate_operand_rounding.py) -- "bf16" keeps bfloat16
+            # where the range matters, in the encoder blocks (with hi + lo MLP weights).
+            refine = "fp32" if self.precision == "fp32" else "fp16"
+            if getattr(self, "_rsb_precision", None) != refine:
                 for mod in self.modules():
                     if isinstance(mod, conv_bn_relu):
-                        mod.precision = self.precision
-                self._rsb_precision = self.precision
+                        mod.precision = refine
+                self._rsb_precision = refine
             # def_fuse only needs total_b: its 25 small convs run on a side stream, concurrently with
             # the (equally launch/latency-bound) C=17 flow encoder and the fusion prologue
             cat = torch.empty((b, 3 * j, h, w), **f32)       # [final_layer1 | final_layer2 | def_heatmaps]
@@ -377,7 +384,7 @@ class OTPose(nn.Module):
                 _lib.dptr(pe1, allow_none=True), _lib.dptr(pe2, allow_none=True), ps1, frames, b, j, t,
                 x1.data_ptr(), x2.data_ptr(), intersection.data_ptr(), prev_b.data_ptr(), st),
                 "otp_fusion_stack_frames")
-            pprec = _lib.precision_code(self.precision)
+            pprec = _lib.precision_code(refine)
 
             def encode(i, enc, fl, xin):
                 stq = _lib.stream_ptr(dev)
@@ -412,7 +419,7 @@ class OTPose(nn.Module):
                 _debug.update(cat=cat, trans=trans, def_heatmaps=def_heatmaps)
             cdef = trans.shape[1]
             ww = 1.0 / len(self.deformable_conv_dilations)
-            prec = _lib.precision_code(self.precision)
+            prec = _lib.precision_code(refine)
             fused = prec != _lib.PREC_FP32 and j == 17 and cdef == 32
             if fused:
                 # offsets / masks never reach HBM: implicit-GEMM conv on tcgen05 feeding the DCN from TMEM

@@ -420,6 +420,34 @@ def test_tensor_core_block_vs_cuda_core_block(b, t, stride, fmt, tol):
     assert torch.equal(got, blk(x, precision=fmt))     # deterministic
 
 
+def test_fp16_operands_saturate_instead_of_overflowing():
+    """IEEE-half operands have a finite range (65504).  With trained checkpoints GELU(hidden), att @ v and
+    the post-ReLU RSB maps are unbounded, so every fp32 -> half operand conversion saturates
+    (cvt.rn.satfinite): a value beyond the range costs accuracy on that element, it never becomes an
+    infinity that would poison the clip.  Weights scaled until hidden / att @ v / conv inputs exceed 6e4."""
+    from otpose_b200.model.blocks import TransformerBlock
+    blk = TransformerBlock(136, 2, n_ds_strides=(1, 1), proj_pdrop=0.1, path_pdrop=0.1)
+    sd = syn.fill_state_dict({k: v.shape for k, v in blk.state_dict().items()}, seed=3)
+    x = cuda(np.random.default_rng(9).standard_normal((2, 136, 1000)).astype(np.float32))
+    for key, factor in (("mlp.0.weight", 3e5), ("attn.value.weight", 1e6), ("attn.value.bias", 1e7)):
+        big = {k: (v * factor if k == key else v) for k, v in sd.items()}
+        blk.load_state_dict(big)
+        blk = blk.cuda().eval()
+        ref = blk(x, precision="fp32")
+        assert ref.abs().max() > 6e4, key                      # the fp32 result really leaves the half range
+        got = blk(x, precision="fp16")
+        assert torch.isfinite(got).all(), key
+    # RSB conv on the tcgen05 path: inputs far beyond the half range
+    m = CHAIN_RSB_BLOCKS(51, 32, 2)
+    m.load_state_dict(syn.fill_state_dict({k: v.shape for k, v in m.state_dict().items()}, seed=5))
+    m = m.cuda().eval()
+    for mod in m.modules():
+        if hasattr(mod, "precision"):
+            mod.precision = "fp16"
+    xs = cuda(np.random.default_rng(10).standard_normal((1, 51, 16, 16)).astype(np.float32)) * 1e6
+    assert torch.isfinite(m(xs)).all()
+
+
 def test_upsample_matches_torch():
     x = torch.randn(2, 5, 13).cuda()
     lib = _lib.load()

@@ -123,3 +123,28 @@ def test_synthetic_is_deterministic_and_nontrivial():
     assert 0.2 < r.amax() < 1.2
     m = syn.synth_margin(64)
     assert m.dtype == torch.int64 and set(np.unique(m.numpy())) <= {0, 1, 2}
+
+
+def test_hrnet_drop_in_matches_reference_golden():
+    """SURVEY 8f rank 3 / configs[1]: the torch HRNet-W48 drop-in reproduces the reference's own module
+    (fixture generated by running model/HRNet.py, oracle/make_golden.py) -- same state-dict layout, fp32 eval
+    output equal to rounding, and the Conv+BN-folded inference copy within 1e-5."""
+    import numpy as np
+    from otpose_b200.model.HRNet import HRNet, hrnet_w48_cfg
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hrnet_w48_64x64.npz"))
+    with open(os.path.join(ROOT, "tests", "golden", "state_dict_manifest.json")) as f:
+        shapes = json.load(f)["hrnet"]
+    net = HRNet(hrnet_w48_cfg()).eval()
+    mine = {k: list(v.shape) for k, v in net.state_dict().items()}
+    assert mine == shapes
+    net.load_state_dict(syn.fill_state_dict(shapes, seed=int(g["seed"])))
+    x = torch.from_numpy(g["x"])
+    with torch.no_grad():
+        out = net(x)
+        feats = net.features(x)
+        folded = net.fold(dtype=torch.float32, memory_format=torch.channels_last)(x)
+    ref = torch.from_numpy(g["out"])
+    scale = ref.abs().max()
+    assert out.shape == ref.shape and feats.shape == (1, 48, 16, 16)
+    assert (out - ref).abs().max() / scale < 1e-6
+    assert (folded - ref).abs().max() / scale < 1e-5
