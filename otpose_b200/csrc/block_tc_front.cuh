@@ -405,13 +405,30 @@ tc_front1_kernel(BlockPack P, const float *__restrict__ x, float *__restrict__ g
 // addresses.
 constexpr int kGpCols = 18, kGpBlocks = kKP / kGpCols, kGpThreads = 2 * kKP;
 static_assert(kGpBlocks * kGpCols == kKP && kGpCols % 2 == 0 && kHS % 2 == 0, "column blocks tile the padded Gram");
+static_assert(kGpThreads == 2 * kKP, "gram_project: two threads per padded channel (the barrier below is CTA-wide)");
 constexpr int kGpElems = (kGramRows * (kGpCols / 2) + kGpThreads - 1) / kGpThreads;   // float2 elements per thread (5)
+constexpr int kGpLd = 20;           // padded row of 18 floats: 80 bytes, float4-aligned broadcast reads
 struct GpSmem {
   float wq[kGramRows][kKP];        // Wq~^T rows 0..136 (cp.async, lands under the chunk reduction)
   float wk[kGpCols][kKP];          // Wk~^T rows j0 .. j0+17
-  float G[kGramRows][kGpCols];
-  float M1[kC][kGpCols + 1];       // odd row stride: conflict-free row-per-thread stores
+  float G[kGramRows][kGpLd];
+  float M1[kC][kGpLd];             // [q channel][column]
 };
+// 18 FMAs against one padded row read as five float4 broadcasts
+__device__ __forceinline__ void gp_fma_row(float (&acc)[kGpCols], float w, const float *row) {
+  const float4 *r4 = reinterpret_cast<const float4 *>(row);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 g = r4[q];
+    acc[4 * q] = fmaf(w, g.x, acc[4 * q]);
+    acc[4 * q + 1] = fmaf(w, g.y, acc[4 * q + 1]);
+    acc[4 * q + 2] = fmaf(w, g.z, acc[4 * q + 2]);
+    acc[4 * q + 3] = fmaf(w, g.w, acc[4 * q + 3]);
+  }
+  const float2 g = *reinterpret_cast<const float2 *>(row + 16);
+  acc[16] = fmaf(w, g.x, acc[16]);
+  acc[17] = fmaf(w, g.y, acc[17]);
+}
 __global__ void __launch_bounds__(kGpThreads)
 gram_project_kernel(const float *__restrict__ gram_part, int nchunk, const float *__restrict__ wqaT,
                     const float *__restrict__ wkaT, float *__restrict__ spart) {
@@ -435,7 +452,7 @@ gram_project_kernel(const float *__restrict__ gram_part, int nchunk, const float
       off[k] = (size_t)(e / (kGpCols / 2)) * kGramLd + 2 * (e % (kGpCols / 2));
       acc[k] = make_float2(0.f, 0.f);
     }
-#pragma unroll 3
+#pragma unroll 5   // 25 independent 8-byte loads in flight per thread: the phase is bound by memory latency
     for (int ch = 0; ch < nchunk; ++ch) {
       float2 v[kGpElems];
 #pragma unroll
@@ -450,32 +467,44 @@ gram_project_kernel(const float *__restrict__ gram_part, int nchunk, const float
 #pragma unroll
     for (int k = 0; k < kGpElems; ++k) {
       const int e = threadIdx.x + k * kGpThreads;
-      if (e < kGramRows * (kGpCols / 2)) {
-        sm.G[e / (kGpCols / 2)][2 * (e % (kGpCols / 2))] = acc[k].x;
-        sm.G[e / (kGpCols / 2)][2 * (e % (kGpCols / 2)) + 1] = acc[k].y;
-      }
+      if (e < kGramRows * (kGpCols / 2))
+        *reinterpret_cast<float2 *>(&sm.G[e / (kGpCols / 2)][2 * (e % (kGpCols / 2))]) = acc[k];
     }
   }
   cp_async_wait<0>();
   __syncthreads();
-  const int half = threadIdx.x / kKP, ch = threadIdx.x % kKP;   // two threads per channel
-  if (ch < kC) {   // M1 row `ch`, columns half*9 .. half*9+8
-    constexpr int kHalfCols = kGpCols / 2;
-    float acc[kHalfCols];
+  // M1 = Wq~ G_J: thread (half, q channel) sums the rows r = half, half + 2, ... (shared memory is read as
+  // float4 broadcasts: one LDS instruction per 4 FMAs, the LSU issue rate is what bounds this kernel)
+  const int half = threadIdx.x / kKP, ch = threadIdx.x % kKP;
+  const bool active = ch < kC;
+  float acc[kGpCols];
 #pragma unroll
-    for (int jj = 0; jj < kHalfCols; ++jj) acc[jj] = 0.f;
+  for (int jj = 0; jj < kGpCols; ++jj) acc[jj] = 0.f;
+  if (active) {
 #pragma unroll 4
-    for (int r = 0; r < kGramRows; ++r) {
-      const float w = sm.wq[r][ch];
+    for (int r = half; r < kGramRows; r += 2) gp_fma_row(acc, sm.wq[r][ch], sm.G[r]);
+  }
+  // the two halves of the r range are added in a fixed order: half 0 stores, half 1 accumulates
+  // (the barriers are outside every branch: all 288 threads reach them)
+  float4 *dst = reinterpret_cast<float4 *>(sm.M1[active ? ch : 0]);
+  if (active && half == 0) {
 #pragma unroll
-      for (int jj = 0; jj < kHalfCols; ++jj) acc[jj] = fmaf(w, sm.G[r][half * kHalfCols + jj], acc[jj]);
-    }
-#pragma unroll
-    for (int jj = 0; jj < kHalfCols; ++jj) sm.M1[ch][half * kHalfCols + jj] = acc[jj];
+    for (int q = 0; q < 4; ++q) dst[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    dst[4] = make_float4(acc[16], acc[17], 0.f, 0.f);
   }
   __syncthreads();
-  // thread = (k output channel m' = column of S within its head, half of that head's 68 rows)
-  if (ch < kC) {
+  if (active && half == 1) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 o = dst[q];
+      dst[q] = make_float4(o.x + acc[4 * q], o.y + acc[4 * q + 1], o.z + acc[4 * q + 2], o.w + acc[4 * q + 3]);
+    }
+    const float4 o = dst[4];
+    dst[4] = make_float4(o.x + acc[16], o.y + acc[17], 0.f, 0.f);
+  }
+  __syncthreads();
+  // S^(J)[i][m] = sum_j M1[i][j] Wk~[h*68 + m][j]: thread = (k channel m', half of that head's 68 rows)
+  if (active) {
     const int h = ch / kHS, m = ch % kHS;
     float wk[kGpCols];
 #pragma unroll
@@ -483,10 +512,19 @@ gram_project_kernel(const float *__restrict__ gram_part, int nchunk, const float
     float *sp = spart + ((size_t)(b * kGpBlocks + J) * kC + h * kHS) * kHS + m;
 #pragma unroll 2
     for (int ii = half * (kHS / 2); ii < (half + 1) * (kHS / 2); ++ii) {
-      const float *mr = sm.M1[h * kHS + ii];
+      const float4 *mr = reinterpret_cast<const float4 *>(sm.M1[h * kHS + ii]);
       float s = 0.f;
 #pragma unroll
-      for (int jj = 0; jj < kGpCols; ++jj) s = fmaf(mr[jj], wk[jj], s);
+      for (int q = 0; q < 4; ++q) {
+        const float4 v = mr[q];
+        s = fmaf(v.x, wk[4 * q], s);
+        s = fmaf(v.y, wk[4 * q + 1], s);
+        s = fmaf(v.z, wk[4 * q + 2], s);
+        s = fmaf(v.w, wk[4 * q + 3], s);
+      }
+      const float4 v = mr[4];
+      s = fmaf(v.x, wk[16], s);
+      s = fmaf(v.y, wk[17], s);
       sp[(size_t)ii * kHS] = s;
     }
   }

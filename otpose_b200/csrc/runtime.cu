@@ -20,7 +20,7 @@ void set_error(const char *fmt, ...) {
 
 namespace otp {
 namespace {
-constexpr int kMaxRecords = 16384;
+constexpr int kMaxRecords = 1 << 19;   // a >= 2 s roofline pass records ~170 scopes per step
 struct Record {
   int id;
   cudaEvent_t a, b;
