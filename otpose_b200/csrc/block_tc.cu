@@ -29,6 +29,8 @@
 // TMEM lane rule: warp w reads lanes 32*(w%4).., so a thread's token is 32*(w%4) + lane and the
 // warps sharing a lane quarter split the accumulator columns (thirds of 48 in tc_front, quarters
 // of 36 in tc_back, halves of 72 in tc_apply).
+#include <string.h>
+
 #include "block_common.cuh"
 #include "block_fold.cuh"
 #include "tc_common.cuh"
@@ -44,31 +46,34 @@ constexpr uint32_t kCS = 128;                 // byte stride between 8-element K
 constexpr uint32_t kRS144 = (kKP / 8) * 128;  // byte stride between 8-row groups, K = 144
 constexpr uint32_t kTile144 = (kTM / 8) * kRS144;  // 36864  [128][144]
 constexpr uint32_t kW144 = (kKP / 8) * kRS144;     // 41472  [144][144]
-constexpr int kNH = 64, kNChunk = 9, kHidPad = kNH * kNChunk;  // hidden 544 -> 576, 9 chunks of 64
-constexpr uint32_t kRS96 = (kNH / 8) * 128;        // 768  (row-group stride of a K = 48 tile)
-constexpr uint32_t kW1c = (kNH / 8) * kRS144;      // 13824  [48][144]
-constexpr uint32_t kW2c = (kKP / 8) * kRS96;       // 13824  [144][48]
-constexpr uint32_t kHTile = (kTM / 8) * kRS96;     // 12288  [128][48]
+constexpr int kNH = 144, kNChunk = 4, kHidPad = kNH * kNChunk;   // hidden 544 -> 576, 4 chunks of 144
+constexpr int kPieceK = 48;                         // K extent of one streamed weight piece (3 UMMA K-steps)
+constexpr uint32_t kRS48 = (kPieceK / 8) * 128;     // 768  row-group stride of a [rows][48] piece
+constexpr uint32_t kPiece = (kKP / 8) * kRS48;      // 13824  [144][48]
+constexpr int kPiecesPerImage = kKP / kPieceK;      // 3
+constexpr int kNumPieces = kPiecesPerImage * (1 + 2 * kNChunk);   // Wp, 4 x W1 chunk, 4 x W2 chunk = 27
 
 // ---- packed tensor-core weights of one block (bytes) ----
-// Three operand-image sets [bf16 hi | fp16 | bf16 lo], then fp32 folded vectors / matrices.  A set holds
-// Wp, W1 chunks, W2 chunks (W1 and W2 contiguous: a chunk index addresses the same offset in every set);
-// the bf16 "lo" set holds bf16(w - bf16(w)) of the W1 / W2 images only: in bfloat16 mode tc_back runs
-// every MLP UMMA chain twice (hi, then lo into the same accumulator) because a weight's rounding error is
-// coherent across tokens (see block_tc_front.cuh; scripts/emulate_operand_rounding.py).
+// Three operand-image sets [bf16 hi | fp16 | bf16 lo], then fp32 folded vectors / matrices.  A set is an
+// array of kNumPieces weight PIECES ([144 rows][48 K], the unit tc_back streams through its ring): Wp
+// (pieces 0..2), W1 chunk c (3 + 3c ..), W2 chunk c (15 + 3c ..); a piece index addresses the same offset
+// in every set.  The bf16 "lo" set holds bf16(w - bf16(w)) of the W1 / W2 pieces only (it starts at piece
+// 3): in bfloat16 mode tc_back runs every MLP UMMA chain twice (hi, then lo into the same accumulator)
+// because a weight's rounding error is coherent across tokens (see block_tc_front.cuh;
+// scripts/emulate_operand_rounding.py).
 struct TcPack {
-  size_t wp, w1 /* [9] */, w2 /* [9] */, img_bytes /* one operand format */, lo /* bf16 lo set: W1, W2 only */;
+  size_t wp, w1 /* [4][3] */, w2 /* [4][3] */, img_bytes /* one operand format */, lo /* bf16 lo set: W1, W2 only */;
   size_t wvp /* fp32 [136][136] Wv * g_v */, bvp /* [144] */, bqp, bkp /* [144] */, b1p /* [576] */;
   size_t wqaT, wkaT /* fp32 [144][144] transposed augmented Wq~ / Wk~ (gram_project_kernel) */, total;
 };
 constexpr TcPack tc_pack_layout() {
   TcPack p{};
   p.wp = 0;
-  p.w1 = p.wp + kW144;
-  p.w2 = p.w1 + (size_t)kNChunk * kW1c;
-  p.img_bytes = p.w2 + (size_t)kNChunk * kW2c;
-  p.lo = 2 * p.img_bytes;                         // + (offset - w1) addresses a lo chunk
-  p.wvp = p.lo + (size_t)2 * kNChunk * kW1c;
+  p.w1 = p.wp + (size_t)kPiecesPerImage * kPiece;
+  p.w2 = p.w1 + (size_t)kNChunk * kPiecesPerImage * kPiece;
+  p.img_bytes = (size_t)kNumPieces * kPiece;
+  p.lo = 2 * p.img_bytes;                         // + (piece - 3) * kPiece addresses a lo piece
+  p.wvp = p.lo + (size_t)(kNumPieces - kPiecesPerImage) * kPiece;
   p.bvp = p.wvp + (size_t)kC * kC * 4;
   p.bqp = p.bvp + kKP * 4;
   p.bkp = p.bqp + kKP * 4;
@@ -177,6 +182,27 @@ __device__ __forceinline__ void tmem_ld48(uint32_t taddr, float (&v)[48]) {
     v[16 + i] = __uint_as_float(r1[i]);
     v[32 + i] = __uint_as_float(r2[i]);
   }
+}
+// 36 consecutive columns (16 + 16 + 4), one wait
+__device__ __forceinline__ void tmem_ld36(uint32_t taddr, float (&v)[36]) {
+  uint32_t r0[16], r1[16], r2[4];
+  tmem_ld16_nw(taddr, r0);
+  tmem_ld16_nw(taddr + 16, r1);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3])
+               : "r"(taddr + 32)
+               : "memory");
+  tmem_wait_ld();
+  reg_fence16(r0);
+  reg_fence16(r1);
+  asm volatile("" : "+r"(r2[0]), "+r"(r2[1]), "+r"(r2[2]), "+r"(r2[3])::"memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    v[i] = __uint_as_float(r0[i]);
+    v[16 + i] = __uint_as_float(r1[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[32 + i] = __uint_as_float(r2[i]);
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r0[16], r1[16];
@@ -394,7 +420,7 @@ void pack_bias_col(int fmt, const float *bias, int row0, int rv, uint8_t *dst, i
 
 constexpr size_t kApplySmem = (size_t)kTile144 + kW144 + kApplyStage;
 static_assert(2 * (kApplySmem + 2048) <= 228 * 1024, "two tc_apply CTAs per SM");
-constexpr size_t kBackSmem = (size_t)2 * kTile144 + kW144 + kBackHB * kHTile + kBackSlots * kW1c + sizeof(BackVec);
+constexpr size_t kBackSmem = (size_t)2 * kTile144 + (size_t)kBackHB * kTile144 + (size_t)kBackSlots * kPiece + sizeof(BackVec);
 static_assert(kBackSmem + 1024 <= 227 * 1024, "tc_back shared memory");
 
 template <bool F16>
@@ -455,12 +481,16 @@ int forward_tc_t(const void *packed_fp32, const void *packed_tc, const float *x,
     LaunchScope ls(K_TC_BACK, st);
     const int total = b * W.tiles;
     const int grid = min(total, num_sms());
+    // y as a 2-D tensor [(clip, channel)][token] written in [136][128] tiles by TMA
+    alignas(64) CUtensorMap ymap;
+    memset(&ymap, 0, sizeof(ymap));
+    const int use_tma = make_tensor_map_2d_f32(&ymap, y, (uint64_t)b * kC, (uint64_t)W.tout, kC, kTM) ? 1 : 0;
     if (stride == 1)
-      tc_back_kernel<F16, false><<<grid, kBackThreads, kBackSmem, st>>>(P, tcw, tcw_lo, x, obuf, y, b, t, W.tout, W.tiles,
-                                                                        g_trace_on);
+      tc_back_kernel<F16, false><<<grid, kBackThreads, kBackSmem, st>>>(P, tcw, tcw_lo, x, obuf, y, ymap, use_tma, b, t,
+                                                                        W.tout, W.tiles, g_trace_on);
     else
-      tc_back_kernel<F16, true><<<grid, kBackThreads, kBackSmem, st>>>(P, tcw, tcw_lo, x, obuf, y, b, t, W.tout, W.tiles,
-                                                                       g_trace_on);
+      tc_back_kernel<F16, true><<<grid, kBackThreads, kBackSmem, st>>>(P, tcw, tcw_lo, x, obuf, y, ymap, use_tma, b, t,
+                                                                       W.tout, W.tiles, g_trace_on);
   }
   return check_launch("block_forward_tc");
 }
@@ -486,16 +516,26 @@ int block_tc_pack(const otp_block_params *p, int c, void *packed_tc, cudaStream_
   if (c != kC) return OTP_OK;
   constexpr TcPack L = tc_pack_layout();
   uint8_t *base = static_cast<uint8_t *>(packed_tc);
-  LaunchScope ls(K_PACK, st, 107);
-  for (int f = 0; f < 3; ++f) {   // 0: bf16 (hi), 1: fp16, 2: bf16 lo terms (W1 / W2 only)
-    uint8_t *d = f < 2 ? base + f * L.img_bytes : base + L.lo - L.w1;
-    const int fmt = f == 1 ? 1 : (f == 2 ? 2 : 0);
-    // LN2 affine folded in: W1' = W1 diag(g2), b1' = b1 + W1 beta2 (fp32 vector below)
-    if (f < 2) pack_image(fmt, p->proj_w, kC, 0, 0, kC, kC, nullptr, d + L.wp, kKP, kKP, st);
-    for (int j = 0; j < kNChunk; ++j) {
-      const int hv = min(kNH, 4 * kC - j * kNH);
-      pack_image(fmt, p->mlp0_w, kC, j * kNH, 0, hv, kC, p->ln2_w, d + L.w1 + (size_t)j * kW1c, kNH, kKP, st);
-      pack_image(fmt, p->mlp3_w, 4 * kC, 0, j * kNH, kC, hv, nullptr, d + L.w2 + (size_t)j * kW2c, kKP, kNH, st);
+  LaunchScope ls(K_PACK, st, 100);
+  // piece (image base, K-slice s) of set f: 0 bf16 (hi), 1 fp16, 2 bf16 lo terms (W1 / W2 only)
+  auto piece = [&](int f, size_t img_off, int s) {
+    uint8_t *set = f < 2 ? base + f * L.img_bytes : base + L.lo - L.w1;
+    return set + img_off + (size_t)s * kPiece;
+  };
+  for (int f = 0; f < 3; ++f) {
+    for (int s = 0; s < kPiecesPerImage; ++s) {
+      const int cv = min(kPieceK, kC - s * kPieceK);   // valid input channels of this K-slice (48, 48, 40)
+      if (f < 2) pack_image(f, p->proj_w, kC, 0, s * kPieceK, kC, cv, nullptr, piece(f, L.wp, s), kKP, kPieceK, st);
+      for (int c = 0; c < kNChunk; ++c) {
+        // W1 chunk c: hidden rows c*144.., K = input channels (LN2 affine folded: W1' = W1 diag(g2))
+        const int hv = max(0, min(kNH, 4 * kC - c * kNH));
+        pack_image(f, p->mlp0_w, kC, c * kNH, s * kPieceK, hv, cv, p->ln2_w,
+                   piece(f, L.w1 + (size_t)c * kPiecesPerImage * kPiece, s), kNH, kPieceK, st);
+        // W2 chunk c: all output rows, K = hidden c*144 + 48 s ..
+        const int kv = max(0, min(kPieceK, 4 * kC - c * kNH - s * kPieceK));
+        pack_image(f, p->mlp3_w, 4 * kC, 0, c * kNH + s * kPieceK, kC, kv, nullptr,
+                   piece(f, L.w2 + (size_t)c * kPiecesPerImage * kPiece, s), kKP, kPieceK, st);
+      }
     }
   }
   scale_cols_kernel<<<ceil_div(kC * kC, 256), 256, 0, st>>>(p->v_w, p->v_norm_w, reinterpret_cast<float *>(base + L.wvp),
@@ -510,14 +550,15 @@ int block_tc_pack(const otp_block_params *p, int c, void *packed_tc, cudaStream_
                                                               1.0f / sqrtf((float)kHS), reinterpret_cast<float *>(base + L.wqaT));
   pack_aug_T_kernel<<<ceil_div(kKP * kKP, 256), 256, 0, st>>>(p->k_w, p->k_norm_w, reinterpret_cast<const float *>(base + L.bkp),
                                                               1.0f, reinterpret_cast<float *>(base + L.wkaT));
-  // biases folded into operand column 136 (tc_back): b_p into Wp, b_1 + W_1 beta_2 into the W1 chunks (hi images;
-  // the lo images carry the bias's bf16 remainder in bfloat16 mode)
+  // biases folded into operand column 136 (= column 40 of K-slice 2): b_p into Wp, b_1 + W_1 beta_2 into the
+  // W1 chunks (the lo pieces carry the bias's bf16 remainder in bfloat16 mode)
   const float *b1f = reinterpret_cast<const float *>(base + L.b1p);
+  constexpr int kBiasSlice = kC / kPieceK, kBiasCol = kC % kPieceK;
   for (int f = 0; f < 3; ++f) {
-    uint8_t *d = f < 2 ? base + f * L.img_bytes : base + L.lo - L.w1;
-    const int fmt = f == 1 ? 1 : (f == 2 ? 2 : 0);
-    if (f < 2) pack_bias_col(fmt, p->proj_b, 0, kC, d + L.wp, kKP, kC, st);
-    for (int j = 0; j < kNChunk; ++j) pack_bias_col(fmt, b1f, j * kNH, kNH, d + L.w1 + (size_t)j * kW1c, kKP, kC, st);
+    if (f < 2) pack_bias_col(f, p->proj_b, 0, kC, piece(f, L.wp, kBiasSlice), kPieceK, kBiasCol, st);
+    for (int c = 0; c < kNChunk; ++c)
+      pack_bias_col(f, b1f, c * kNH, kNH, piece(f, L.w1 + (size_t)c * kPiecesPerImage * kPiece, kBiasSlice), kPieceK,
+                    kBiasCol, st);
   }
   return check_launch("block_tc_pack");
 }

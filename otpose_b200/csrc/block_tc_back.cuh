@@ -2,20 +2,26 @@
 // 441-452) on tcgen05 tensor cores.  Included by block_tc.cu inside its anonymous namespace
 // (uses its tile constants, TcPack and gelu_pair).
 //
-// One persistent, warp-specialised CTA per SM (576 threads, ~218 KB shared memory, 512 TMEM columns):
+// One persistent, warp-specialised CTA per SM (576 threads, ~217 KB shared memory, 432 TMEM columns):
 //   warp 16            MMA ISSUER (converged warp, single instructions elect-predicated): issues every
 //                      tcgen05.mma and signals the epilogue through tcgen05.commit -> mbarrier.
-//   warp 17            TMA PRODUCER: streams the 9 + 9 W1 / W2 chunk images with cp.async.bulk through a
-//                      4-slot ring that runs ahead across tile boundaries.  Wp stays resident.
+//   warp 17            TMA PRODUCER: streams the weight images as 13.8 KB K-slices ([144 rows][48 K]) with
+//                      cp.async.bulk through a 5-slot ring that runs ahead across tile boundaries.
 //   warps 0-15         EPILOGUE: thread (q4, lane, quarter) owns token 32*q4 + lane and 36 of the 144
 //                      accumulator columns; in the MLP the warps form two groups (quarter parity) that
-//                      take alternate hidden chunks, 32 of the 64 hidden columns per thread, each group
+//                      take alternate hidden chunks, 72 of the 144 hidden columns per thread, each group
 //                      with its own GELU tile in shared memory.
+//
+// The hidden dimension (544 -> 576) is cut into FOUR chunks of 144: every UMMA of the kernel is
+// M128 x N144 x K16 (73 cycles, the tensor pipe's full rate; the 64-wide chunks of the first version ran
+// their N = 64 UMMAs at 52 cycles against an ideal 32 -- shared-memory operand reads bound them) and a
+// tile has 4 epilogue <-> tensor-core hand-offs instead of 9.  TMEM: y accumulator (144 columns) + two
+// hidden accumulators (2 x 144); the proj accumulator of the NEXT tile aliases hidden accumulator 0, which
+// is idle between GELU(chunk 2) and the next tile's first W1 chunk.
+//
 // Software pipeline across tiles: while tile n is in its MLP, the out2 tile of tile n+1 is copied
-// into the other operand buffer, its skip rows are prefetched into L2 and its proj UMMA runs into a
-// second accumulator, so a tile starts with its proj result already in TMEM.  Within the MLP, W1
-// chunk j+3 is issued as soon as GELU(chunk j) has drained its TMEM buffer and there is one GELU tile
-// per warp group: the epilogue warps do not wait for tensor-core round trips in steady state.
+// into the other operand buffer, its skip rows are prefetched into L2 and its proj UMMAs run, so a tile
+// starts with its proj result already in TMEM.
 //
 //  * out2 tile: the (nh, T', hs) 16-bit attention output re-read as (C, T') is a set of 256-byte
 //    runs (128 tokens of one channel), copied with 16-byte cp.async straight into a
@@ -24,9 +30,14 @@
 //  * LN2(u) tile: column 136 = 1, W1 image column 136 = b_1 + W_1 beta_2 (bias folded).
 //  * u (the residual stream after attention) stays in registers across the MLP (36 values per
 //    thread), so y is written exactly once.
+//  * y leaves through shared memory: the fp32 [channel][token] tile is assembled in the (by then idle)
+//    GELU tiles and written with one tensor-map TMA store (cp.async.bulk.tensor.2d, UTMASTG) per tile,
+//    asynchronously -- 36 scalar stores per thread kept the epilogue warps blocked on the SM's 32 B/clk
+//    store path for ~2.5 k cycles per tile while the tensor pipe idled (and one 512-byte cp.async.bulk per
+//    channel cost the issuing warp ~80 cycles per lane).
 //
 // Optional phase trace (otp_debug_trace): CTA 0 records (clock64 << 8 | event) for epilogue warp 0
-// (row 0) and the control warp (row 1).
+// (row 0), the control warp (row 1) and epilogue warp 15 (row 2).
 constexpr int kTraceLen = 2048;
 __device__ unsigned long long g_back_trace[4][kTraceLen];   // tc_back: epilogue warp 0, control, epilogue warp 15;
                                                             // row 3: tc_front compute warp 0
@@ -40,20 +51,17 @@ struct Tracer {
 
 constexpr int kBackEpi = 512;                 // epilogue threads (warps 0..15)
 constexpr int kBackThreads = kBackEpi + 64;   // + MMA warp (16) + TMA producer warp (17)
-constexpr int kBackSlots = 4;                 // weight ring slots of kW1c == kW2c bytes: every MLP chunk consumes two
-                                              // (W2_j, W1_j+3), so four slots keep the TMA stream two chunks ahead
+constexpr int kBackSlots = 5;                 // ring slots of one weight piece each
 constexpr int kBackHB = 2;                    // GELU tiles in shared memory: one per epilogue warp group (chunk parity)
-constexpr int kBackTH = 3;                    // hidden accumulators in TMEM:
-                                              // W1 chunk c+3 is issued when GELU(c) is done
-constexpr int kBackLoads = 2 * kNChunk;       // weight chunk loads per tile
+constexpr int kBackTH = 2;                    // hidden accumulators in TMEM
 constexpr int kCQ = kKP / 4;                  // 36 accumulator columns per epilogue thread
-constexpr int kHQ = kNH / 4;                  // 16 hidden columns per epilogue thread and chunk
-static_assert(kW1c == kW2c, "W1 and W2 chunk images share the ring slots");
-static_assert(kNChunk == 9, "weight chunk order and next-tile staging schedule below");
-static_assert(kHQ == 16 && kCQ == 36, "epilogue column split");
+constexpr int kHC = kNH / 2;                  // 72 hidden columns per epilogue thread and chunk
+constexpr int kGroupsPerTile = 9;             // weight images of a tile in MMA order (see back_group_base)
+static_assert(kNChunk == 4 && kNH == kKP, "weight group order and TMEM aliasing below assume 4 chunks of 144");
+static_assert(kCQ == 36 && kHC == 72, "epilogue column split");
 
 struct BackVec {
-  float sa[kKP], b2[kKP], sm[kKP];
+  float sa[kKP], b2[kKP] /* s_m * b_2 */, sm[kKP];   // read as float4 broadcasts (16-byte aligned, cq % 4 == 0)
   float part[2][4][kTM];
 };
 struct BackBars {
@@ -66,11 +74,10 @@ struct BackBars {
   uint64_t yfull;             // a tile's last W2 chunk MMA done: y accumulator complete (one phase per tile)
   uint64_t wfull[kBackSlots];    // TMA arrival of a ring slot
   uint64_t wempty[kBackSlots];   // the MMAs reading a ring slot are done
-  uint64_t wpfull;       // TMA arrival of Wp
 };
 constexpr uint32_t kRSa = (kTM / 8) * 128;   // 2048: channel-group stride of the token-contiguous out2 tile
-constexpr uint32_t kRSH = (kNH / 8) * 128;   // row-group stride of a K = kNH tile
 static_assert(kRSa * (kKP / 8) == kTile144, "out2 tile and LN2(u) tile share one buffer");
+static_assert((size_t)kC * kTM * 4 <= (size_t)kBackHB * kTile144, "the fp32 y tile is staged in the GELU tiles");
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -119,45 +126,50 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kBackEpi) : "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// Weight chunk q of the per-tile MMA order W1_0, W1_1, W1_2, {W2_j, W1_{j+3}}_{j=0..5}, W2_6, W2_7, W2_8.
-__device__ __forceinline__ size_t back_chunk_offset(const TcPack &L, int q) {
-  if (q < 3) return L.w1 + (size_t)q * kW1c;
-  if (q >= 15) return L.w2 + (size_t)(q - 9) * kW2c;
-  return (q & 1) ? L.w2 + (size_t)((q - 3) >> 1) * kW2c : L.w1 + (size_t)((q + 3) >> 1) * kW1c;
+// Weight image g of the per-tile MMA order  W1_0, W1_1, W2_0, W1_2, W2_1, W1_3, W2_2, Wp(next tile), W2_3
+// -> index of its first K-slice in the packed piece array (Wp: 0..2, W1_c: 3 + 3c, W2_c: 15 + 3c).
+__device__ __forceinline__ int back_group_base(int g) {
+  switch (g) {
+    case 0: return 3;
+    case 1: return 6;
+    case 2: return 15;
+    case 3: return 9;
+    case 4: return 18;
+    case 5: return 12;
+    case 6: return 21;
+    case 7: return 0;
+    default: return 24;
+  }
 }
 
 template <bool F16, bool S2>
 __global__ void __launch_bounds__(kBackThreads, 1)
 tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const uint8_t *__restrict__ tcw_lo,
-               const float *__restrict__ x,
-               const unsigned short *__restrict__ obuf, float *__restrict__ y, int B, int T, int Tout, int tiles,
-               int trace) {
+               const float *__restrict__ x, const unsigned short *__restrict__ obuf, float *__restrict__ y,
+               const __grid_constant__ CUtensorMap ymap, int use_tma, int B, int T, int Tout, int tiles, int trace) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *abuf = smem;                      // 2 x { out2 tile (token-contiguous), then LN2(u) (channel-contiguous) }
-  uint8_t *wpb = abuf + 2 * kTile144;        // Wp, resident
-  uint8_t *hbuf = wpb + kW144;               // kBackHB x GELU(hidden chunk)
-  uint8_t *ring = hbuf + kBackHB * kHTile;   // kBackSlots weight chunk slots
-  BackVec *V = reinterpret_cast<BackVec *>(ring + kBackSlots * kW1c);
+  uint8_t *hbuf = abuf + 2 * kTile144;       // kBackHB x GELU(hidden chunk) [128][144]; after the MLP: the y tile
+  uint8_t *ring = hbuf + kBackHB * kTile144; // kBackSlots weight pieces
+  BackVec *V = reinterpret_cast<BackVec *>(ring + kBackSlots * kPiece);
   __shared__ BackBars bars;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr TcPack L = tc_pack_layout();
-  // bfloat16 mode: every W1 / W2 chunk is streamed and multiplied twice (hi term, then the lo remainder
+  // bfloat16 mode: every W1 / W2 piece is streamed and multiplied twice (hi term, then the lo remainder
   // into the same accumulator) -- a rounded weight perturbs every token coherently, see block_tc_front.cuh
   constexpr bool kSplit = !F16;
-  constexpr int kPasses = kSplit ? 2 : 1;
   const int total = B * tiles;
   const int ntile = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
 
   for (int n = threadIdx.x; n < kKP; n += kBackThreads) {
     V->sa[n] = P.sa[n];
-    V->b2[n] = P.b2[n];
+    V->b2[n] = P.sm[n] * P.b2[n];   // s_m * b_2: added to u once the LN2 tile is written, so that E3 is one FMA
     V->sm[n] = P.sm[n];
   }
   if (threadIdx.x == 0) {
     mbar_init(&bars.lnfull, kBackEpi / 32);
     mbar_init(&bars.pfull, 1);
-    mbar_init(&bars.wpfull, 1);
     mbar_init(&bars.yfull, 1);
 #pragma unroll
     for (int i = 0; i < kBackTH; ++i) mbar_init(&bars.thfull[i], 1);
@@ -181,112 +193,103 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const uint8_t *__re
   tc_fence_after();
   const uint32_t tm = tmem_slot;
   const uint32_t t_y = tm;             // MLP output accumulator (144 columns)
-  const uint32_t t_p = tm + kKP;       // proj accumulator of the NEXT tile (144 columns)
-  const uint32_t t_h = tm + 2 * kKP;   // kBackTH x hidden chunk accumulator (kNH columns each)
+  const uint32_t t_h = tm + kKP;       // kBackTH x hidden chunk accumulator (144 columns each)
+  const uint32_t t_p = t_h;            // proj accumulator of the NEXT tile == hidden accumulator 0 (see header)
   constexpr uint32_t kFmt = F16 ? 0u : 1u;
 
   if (warp == kBackEpi / 32 + 1) {
     // =============================================================== TMA PRODUCER
-    // Wp once, then the weight chunk stream of every tile of this CTA through the ring; a slot is
-    // refilled as soon as the MMAs that read it have completed (wempty), so the stream runs up to
-    // three chunks ahead of the tensor core, across tile boundaries.
-    if (ntile > 0) tma_elect(wpb, tcw + L.wp, kW144, &bars.wpfull);
-    const int nload = kBackLoads * ntile;
-    int q = 0, slot = 0;
+    // The piece stream in exactly the order the MMA issuer consumes it; a slot is refilled as soon as the
+    // UMMAs that read it have completed (wempty), so the stream runs up to five pieces ahead of the tensor
+    // core, across tile boundaries.
+    int slot = 0;
     uint32_t round = 0;   // loads / kBackSlots
-    for (int gq = 0; gq < nload; ++gq) {
-      const size_t off = back_chunk_offset(L, q);
-#pragma unroll
-      for (int pass = 0; pass < kPasses; ++pass) {
-        if (round > 0) mbar_wait(&bars.wempty[slot], (round - 1) & 1);
-        tma_elect(ring + slot * kW1c, pass ? tcw_lo + (off - L.w1) : tcw + off, kW1c, &bars.wfull[slot]);
-        if (++slot == kBackSlots) {
-          slot = 0;
-          ++round;
-        }
-      }
-      if (++q == kBackLoads) q = 0;
-    }
-  } else if (warp == kBackEpi / 32) {
-    // =============================================================== MMA ISSUER
-    const uint32_t idesc144 = make_idesc_16(kKP, false, false, kFmt);
-    const uint32_t idescP = make_idesc_16(kKP, true, false, kFmt);   // A = out2 tile, token-contiguous
-    const uint32_t idescH = make_idesc_16(kNH, false, false, kFmt);
-    const uint32_t ab = smem_u32(abuf), rr = smem_u32(ring), hb = smem_u32(hbuf), wp = smem_u32(wpb);
-    Tracer tr{(trace && blockIdx.x == 0 && lane == 0) ? g_back_trace[1] : nullptr, 0};
-    int slot = 0;          // ring slot of the next weight chunk (chunks are consumed in load order)
-    uint32_t round = 0;
-    // wait for the next chunk of the stream; returns its shared-memory address
-    auto next_chunk = [&]() -> uint32_t {
-      mbar_wait(&bars.wfull[slot], round & 1);
-      return rr + slot * kW1c;
-    };
-    auto release_chunk = [&]() {   // after the MMAs reading it have been issued
-      commit_elect(&bars.wempty[slot]);
+    auto load = [&](const uint8_t *src) {
+      if (round > 0) mbar_wait(&bars.wempty[slot], (round - 1) & 1);
+      tma_elect(ring + slot * kPiece, src, kPiece, &bars.wfull[slot]);
       if (++slot == kBackSlots) {
         slot = 0;
         ++round;
       }
     };
+    if (ntile > 0) {
+#pragma unroll 1
+      for (int s = 0; s < 3; ++s) load(tcw + L.wp + (size_t)s * kPiece);
+    }
+#pragma unroll 1
+    for (int it = 0; it < ntile; ++it) {
+#pragma unroll 1
+      for (int g = 0; g < kGroupsPerTile; ++g) {
+        if (g == 7 && it + 1 >= ntile) continue;   // no next tile: no Wp
+        const int base = back_group_base(g);
+#pragma unroll 1
+        for (int s = 0; s < 3; ++s) {
+          load(tcw + (size_t)(base + s) * kPiece);
+          if (kSplit && g != 7) load(tcw_lo + (size_t)(base + s - 3) * kPiece);
+        }
+      }
+    }
+  } else if (warp == kBackEpi / 32) {
+    // =============================================================== MMA ISSUER
+    const uint32_t idesc144 = make_idesc_16(kKP, false, false, kFmt);
+    const uint32_t idescP = make_idesc_16(kKP, true, false, kFmt);   // A = out2 tile, token-contiguous
+    const uint32_t ab = smem_u32(abuf), rr = smem_u32(ring), hb = smem_u32(hbuf);
+    Tracer tr{(trace && blockIdx.x == 0 && lane == 0) ? g_back_trace[1] : nullptr, 0};
+    int slot = 0;          // ring slot of the next weight piece (pieces are consumed in load order)
+    uint32_t round = 0;
+    // One weight image = 3 K-slices of 48 (x 2 in bfloat16 mode: hi, lo): D (+)= A[:, K] . W[:, K]^T.
+    // a_step: byte step of the A operand per K-step of 16; (a_lbo, a_sbo): its descriptor strides.
+    auto run_group = [&](uint32_t d_tmem, uint32_t a_base, uint32_t a_step, uint32_t a_lbo, uint32_t a_sbo,
+                         uint32_t idesc, bool fresh, bool split) {
+#pragma unroll 1
+      for (int s = 0; s < 3; ++s) {
+#pragma unroll 1
+        for (int pass = 0; pass < (split ? 2 : 1); ++pass) {
+          mbar_wait(&bars.wfull[slot], round & 1);
+          const uint32_t w = rr + slot * kPiece;
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+            umma_elect(d_tmem, make_desc(a_base + (3 * s + k) * a_step, a_lbo, a_sbo),
+                       make_desc(w + k * 2 * kCS, kCS, kRS48), idesc, !(fresh && s == 0 && k == 0 && pass == 0));
+          commit_elect(&bars.wempty[slot]);
+          if (++slot == kBackSlots) {
+            slot = 0;
+            ++round;
+          }
+        }
+      }
+    };
     auto proj = [&](int it) {          // D_p = [out2 | 1] . [Wp | b_p]^T for tile `it`
       mbar_wait(&bars.aofull[it & 1], (it >> 1) & 1);
       tc_fence_after();
-      const uint32_t aa = ab + (it & 1) * kTile144;
-#pragma unroll
-      for (int s = 0; s < kKP / 16; ++s)
-        umma_elect(t_p, make_desc(aa + s * 2 * kRSa, kRSa, kCS), make_desc(wp + s * 2 * kCS, kCS, kRS144), idescP, s > 0);
+      run_group(t_p, ab + (it & 1) * kTile144, 2 * kRSa, kRSa, kCS, idescP, true, false);
       commit_elect(&bars.pfull);
     };
-    if (ntile > 0) {
-      mbar_wait(&bars.wpfull, 0);
-      proj(0);
-    }
+    if (ntile > 0) proj(0);
     for (int it = 0; it < ntile; ++it) {
-      const int c0 = kNChunk * it;
       const uint32_t aa = ab + (it & 1) * kTile144;
-      auto mma1 = [&](int c) {   // D_h[c%3] = [LN2(u) | 1] . [W1_j | b1_j]^T
-#pragma unroll
-        for (int pass = 0; pass < kPasses; ++pass) {
-          const uint32_t w1 = next_chunk();
-#pragma unroll
-          for (int s = 0; s < kKP / 16; ++s)
-            umma_elect(t_h + (c % kBackTH) * kNH, make_desc(aa + s * 2 * kCS, kCS, kRS144),
-                       make_desc(w1 + s * 2 * kCS, kCS, kRS144), idescH, (pass > 0 || s > 0));
-          release_chunk();
-        }
-        commit_elect(&bars.thfull[c % kBackTH]);
+      auto mma1 = [&](int c) {   // D_h[c&1] = [LN2(u) | 1] . [W1_c | b1_c]^T
+        run_group(t_h + (c & 1) * kNH, aa, 2 * kCS, kCS, kRS144, idesc144, true, kSplit);
+        commit_elect(&bars.thfull[c & 1]);
       };
       tr(0);
       mbar_wait(&bars.lnfull, it & 1);
       tc_fence_after();
       tr(5);
-      mma1(c0);
-      mma1(c0 + 1);
-      mma1(c0 + 2);
+      mma1(0);
+      mma1(1);
       tr(6);
 #pragma unroll 1
-      for (int j = 0; j < kNChunk; ++j) {
-        const int c = c0 + j;
-        mbar_wait(&bars.hbfull[c % kBackHB], (c / kBackHB) & 1);
-        tr(10 + j);
+      for (int c = 0; c < kNChunk; ++c) {
+        mbar_wait(&bars.hbfull[c & 1], (c >> 1) & 1);   // two uses of each GELU tile per tile: parity = c >> 1
+        tr(10 + c);
         tc_fence_after();
-        const uint32_t hh = hb + (c % kBackHB) * kHTile;
-#pragma unroll
-        for (int pass = 0; pass < kPasses; ++pass) {
-          const uint32_t w2 = next_chunk();
-          if (pass == 0) tr(30 + j);
-#pragma unroll
-          for (int s = 0; s < kNH / 16; ++s)
-            umma_elect(t_y, make_desc(hh + s * 2 * kCS, kCS, kRSH), make_desc(w2 + s * 2 * kCS, kCS, kRSH), idesc144,
-                       (j > 0 || s > 0 || pass > 0));
-          release_chunk();
-        }
-        commit_elect(&bars.hbfree[c % kBackHB]);
-        if (j == kNChunk - 1) commit_elect(&bars.yfull);
-        if (j + 3 < kNChunk) mma1(c + 3);   // t_h[c%3] was drained by GELU(chunk c) before hbfull[c%3]
-        if (j == kNChunk - 2 && it + 1 < ntile) proj(it + 1);   // its out2 tile is published at chunk 6;
-                                                                // E1 of this tile has left t_p (lnfull above)
-        tr(50 + j);
+        run_group(t_y, hb + (c & 1) * kTile144, 2 * kCS, kCS, kRS144, idesc144, c == 0, kSplit);
+        commit_elect(&bars.hbfree[c & 1]);
+        if (c == kNChunk - 1) commit_elect(&bars.yfull);
+        if (c + 2 < kNChunk) mma1(c + 2);   // t_h[c&1] was drained by GELU(chunk c) before hbfull[c&1]
+        if (c == 2 && it + 1 < ntile) proj(it + 1);   // t_p == t_h[0]: idle from GELU(chunk 2) to the next W1_0
+        tr(50 + c);
       }
     }
   } else {
@@ -297,22 +300,22 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const uint8_t *__re
     const bool aligned = (Tout & 7) == 0;
     Tracer tr{(trace && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 15)) ? g_back_trace[warp ? 2 : 0] : nullptr, 0};
     // out2 tile of tile g: channel c of the (C, T') view is the contiguous run obuf_b[c*T' + t0 ...].
-    // The copy is cut into kStageParts slices (part < 0: all of them) so that the next tile's slices
-    // can be issued one per MLP chunk, in the slack the epilogue warps have there anyway.
+    // The copy is cut into kStageParts slices so that the next tile's slices can be issued between the
+    // MLP chunks, in the slack the epilogue warps have there anyway.
     constexpr int kStageParts = (kC * 16 + kBackEpi - 1) / kBackEpi;   // 5
-    auto stage_out2 = [&](int g, uint8_t *a, int part) {
+    auto stage_out2 = [&](int g, uint8_t *a, int part_lo, int part_hi) {
       const int b = g / tiles, t0 = (g % tiles) * kTM, nvalid = min(kTM, Tout - t0);
       const unsigned short *ob = obuf + (size_t)b * kC * Tout + t0;
       if (aligned) {
         // lane -> (channel within its group of 8, 8-token run j): 8 consecutive lanes fill one
         // 128-byte row of a core-matrix block (no shared-memory bank conflicts among them)
-        for (int k = (part < 0 ? 0 : part); k < (part < 0 ? kStageParts : part + 1); ++k) {
+        for (int k = part_lo; k < part_hi; ++k) {
           const int i = threadIdx.x + k * kBackEpi;
           const int c = ((i >> 7) << 3) | (i & 7), j = (i >> 3) & 15;
           if (i < kC * 16 && j * 8 < nvalid)
             cp_async16(a + (c >> 3) * kRSa + j * 128 + (c & 7) * 16, ob + (size_t)c * Tout + j * 8);
         }
-      } else if (part <= 0) {   // T' not a multiple of 8: runs are not 16-byte aligned, element copies
+      } else if (part_lo == 0) {   // T' not a multiple of 8: runs are not 16-byte aligned, element copies
         for (int i = 0; i < kCQ; ++i) {
           const int c = cq + i;
           if (c < kC)
@@ -320,7 +323,7 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const uint8_t *__re
                 tok < nvalid ? __ldg(ob + (size_t)c * Tout + tok) : (unsigned short)0;
         }
       }
-      if (part <= 0 && threadIdx.x < 128) {   // channels 136..143: a row of ones (bias), then zeros
+      if (part_lo == 0 && threadIdx.x < 128) {   // channels 136..143: a row of ones (bias), then zeros
         const uint32_t one2 = F16 ? 0x3C003C00u : 0x3F803F80u;
         const uint32_t v = (threadIdx.x & 7) == 0 ? one2 : 0u;
         *reinterpret_cast<uint4 *>(a + (kC / 8) * kRSa + threadIdx.x * 16) = make_uint4(v, v, v, v);
@@ -334,16 +337,16 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const uint8_t *__re
       if (lane == 0) mbar_arrive(&bars.aofull[it & 1]);
     };
     if (ntile > 0) {
-      stage_out2(blockIdx.x, abuf, -1);
+      stage_out2(blockIdx.x, abuf, 0, kStageParts);
       publish_out2(0);
     }
+    bool y_store_pending = false;   // this thread has a bulk store of the previous tile's y in flight
     for (int it = 0; it < ntile; ++it) {
       const int g = blockIdx.x + it * gridDim.x;
       const int b = g / tiles, tile = g % tiles;
       const int t0 = tile * kTM, nvalid = min(kTM, Tout - t0);
       const bool live = tok < nvalid;
       const int tt = t0 + tok;
-      const int c0 = kNChunk * it;
       uint8_t *a = abuf + (it & 1) * kTile144;
       tr(0);
       // ---- skip path pool_skip(x) (rows prefetched into L2 during the previous tile's MLP) ----
@@ -371,23 +374,23 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const uint8_t *__re
           }
 #pragma unroll
           for (int i0 = 0; i0 < kCQ; i0 += 9) {
-            float2 ab[9];
+            float2 ab2[9];
 #pragma unroll
             for (int e = 0; e < 9; ++e) {
               const float *p = xr + (size_t)(i0 + e) * T;
-              ab[e] = make_float2(0.f, -3.402823466e38f);
+              ab2[e] = make_float2(0.f, -3.402823466e38f);
               if (cq + i0 + e < kC && live) {
                 if (pair_ok) {
-                  ab[e] = __ldg(reinterpret_cast<const float2 *>(p));
+                  ab2[e] = __ldg(reinterpret_cast<const float2 *>(p));
                 } else {
-                  ab[e].x = __ldg(p);
-                  if (has_r) ab[e].y = __ldg(p + 1);
+                  ab2[e].x = __ldg(p);
+                  if (has_r) ab2[e].y = __ldg(p + 1);
                 }
               }
             }
 #pragma unroll
             for (int e = 0; e < 9; ++e)
-              u[i0 + e] = (cq + i0 + e < kC && live) ? fmaxf(u[i0 + e], fmaxf(ab[e].x, ab[e].y)) : 0.f;
+              u[i0 + e] = (cq + i0 + e < kC && live) ? fmaxf(u[i0 + e], fmaxf(ab2[e].x, ab2[e].y)) : 0.f;
           }
         }
       }
@@ -398,24 +401,22 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const uint8_t *__re
       // ---- u = skip(x) + s_a * (proj + b_p): stays in registers across the MLP (36 per thread) ----
       {
         float s = 0.f;
-        auto piece = [&](const float *v, int i0, int cnt) {
-#pragma unroll
-          for (int e = 0; e < cnt; ++e) {
-            const int i = i0 + e, n = cq + i;
-            const float val = (n < kC && live) ? fmaf(V->sa[n], v[e], u[i]) : 0.f;
-            u[i] = val;
-            s += val;
-          }
-        };
         {
-          float v[16];
-          tmem_ld16(tcol(t_p, q4, cq), v);
-          piece(v, 0, 16);
-          tmem_ld16(tcol(t_p, q4, cq + 16), v);
-          piece(v, 16, 16);
-          float v4[4];
-          tmem_ld4(tcol(t_p, q4, cq + 32), v4);
-          piece(v4, 32, 4);
+          float v[kCQ];
+          tmem_ld36(tcol(t_p, q4, cq), v);   // the three loads issued back to back, one wait
+          const float4 *sa4 = reinterpret_cast<const float4 *>(V->sa + cq);
+#pragma unroll
+          for (int q = 0; q < kCQ / 4; ++q) {
+            const float4 w = sa4[q];
+            const float ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = 4 * q + e, n = cq + i;
+              const float val = (n < kC && live) ? fmaf(ww[e], v[i], u[i]) : 0.f;
+              u[i] = val;
+              s += val;
+            }
+          }
         }
         // per-thread (mean, M2) over its n_q valid columns, combined across the 4 quarters with the
         // parallel-variance formula: one barrier, no E[x^2] - mean^2 cancellation
@@ -432,6 +433,7 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const uint8_t *__re
       }
       tr(4);
       epi_bar_sync();
+      tr(8);
       float mu, var;
       {
         const float m0 = V->part[0][0][tok], m1 = V->part[0][1][tok], m2 = V->part[0][2][tok], m3 = V->part[0][3][tok];
@@ -463,54 +465,85 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const uint8_t *__re
         hv2.x = (quarter & 1) ? pack16x2<F16>(h[0], h[1]) : pack16x2<F16>(h[32], h[33]);
         hv2.y = (quarter & 1) ? pack16x2<F16>(h[2], h[3]) : pack16x2<F16>(h[34], h[35]);
         *reinterpret_cast<uint2 *>(a + cm_offset(tok, cq + ((quarter & 1) ? 0 : 32), kRS144, kCS)) = hv2;
+        const float4 *b4 = reinterpret_cast<const float4 *>(V->b2 + cq);   // u += s_m * b_2 (LN2 is done with u)
+#pragma unroll
+        for (int q = 0; q < kCQ / 4; ++q) {
+          const float4 w = b4[q];
+          u[4 * q] += w.x;
+          u[4 * q + 1] += w.y;
+          u[4 * q + 2] += w.z;
+          u[4 * q + 3] += w.w;
+        }
       }
+      // the previous tile's y tile (staged in the GELU tiles) has been read by its bulk stores: the GELU
+      // tiles are only rewritten behind the MMAs that this arrival releases
+      if (y_store_pending) {
+        tma_store_wait_read();
+        y_store_pending = false;
+      }
+      tr(6);
       fence_async_smem();
+      tr(7);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.lnfull);
       tr(5);
       // ---- MLP epilogue: GELU(hidden chunk) -> 16-bit H tile.  The 16 warps form two groups of 8 that
-      //      take ALTERNATE chunks (32 of the 64 hidden columns per thread): the chain of one chunk
+      //      take ALTERNATE chunks (72 of the 144 hidden columns per thread): the chain of one chunk
       //      (accumulator wait -> tcgen05.ld -> GELU -> shared stores -> proxy fence -> arrive) overlaps
-      //      the other group's chain of the next chunk instead of serialising in the same warps.  A
-      //      group waits on every other phase of thfull / hbfree; that is safe because it has seen chunk
-      //      c-2 (issued after chunk c-3, the previous phase of the same slot) before it waits for c. ----
+      //      the other group's chain of the next chunk instead of serialising in the same warps. ----
       const bool has_next = it + 1 < ntile;
 #pragma unroll 1
-      for (int j = 0; j < kNChunk; ++j) {
-        const int c = c0 + j;
+      for (int c = 0; c < kNChunk; ++c) {
         if ((c & 1) == (quarter & 1)) {
-          const uint32_t par = (c / kBackTH) & 1;
-          mbar_wait(&bars.thfull[c % kBackTH], par);
-          if (c >= kBackHB)   // W2 chunk c-2 (this group's previous chunk) has consumed hbuf[c%2]
-            mbar_wait(&bars.hbfree[c % kBackHB], ((c / kBackHB) & 1) ^ 1);
+          mbar_wait(&bars.thfull[c & 1], (c >> 1) & 1);
+          if (it > 0 || c >= kBackHB)   // the W2 UMMAs of this GELU tile's previous use have consumed it
+            mbar_wait(&bars.hbfree[c & 1], ((c >> 1) + 1) & 1);
           tc_fence_after();
-          tr(10 + j);
-          const int hcol = (quarter >> 1) * 2 * kHQ;   // 32 hidden columns of this thread
-          float hv[2 * kHQ];
-          tmem_ld32(tcol(t_h + (c % kBackTH) * kNH, q4, hcol), hv);
-          uint8_t *dst = hbuf + (c % kBackHB) * kHTile + cm_offset(tok, hcol, kRSH, kCS);
+          tr(10 + c);
+          const int hcol = (quarter >> 1) * kHC;   // 72 hidden columns of this thread
+          const uint32_t th = tcol(t_h + (c & 1) * kNH, q4, hcol);
+          uint8_t *dst = hbuf + (c & 1) * kTile144 + cm_offset(tok, hcol, kRS144, kCS);
+          // 72 columns as 4 x 16 + 8: the tcgen05.ld of piece i+1 is in flight while piece i is processed
+          uint32_t r[2][16];
+          tmem_ld16_nw(th, r[0]);
 #pragma unroll
-          for (int gg = 0; gg < 4; ++gg) {
-            const float *v = hv + gg * 8;
-            uint4 w4;
-            w4.x = gelu_pair<F16>(v[0], v[1]);
-            w4.y = gelu_pair<F16>(v[2], v[3]);
-            w4.z = gelu_pair<F16>(v[4], v[5]);
-            w4.w = gelu_pair<F16>(v[6], v[7]);
-            *reinterpret_cast<uint4 *>(dst + gg * kCS) = w4;
+          for (int pc = 0; pc < 5; ++pc) {
+            tmem_wait_ld();
+            reg_fence16(r[pc & 1]);
+            if (pc + 1 < 4) {
+              tmem_ld16_nw(th + 16 * (pc + 1), r[(pc + 1) & 1]);
+            } else if (pc + 1 == 4) {
+              uint32_t(&q8)[16] = r[(pc + 1) & 1];
+              asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                           : "=r"(q8[0]), "=r"(q8[1]), "=r"(q8[2]), "=r"(q8[3]), "=r"(q8[4]), "=r"(q8[5]), "=r"(q8[6]),
+                             "=r"(q8[7])
+                           : "r"(th + 64)
+                           : "memory");
+            }
+            const uint32_t(&rv)[16] = r[pc & 1];
+#pragma unroll
+            for (int gg = 0; gg < (pc < 4 ? 2 : 1); ++gg) {
+              uint4 w4;
+              w4.x = gelu_pair<F16>(__uint_as_float(rv[8 * gg]), __uint_as_float(rv[8 * gg + 1]));
+              w4.y = gelu_pair<F16>(__uint_as_float(rv[8 * gg + 2]), __uint_as_float(rv[8 * gg + 3]));
+              w4.z = gelu_pair<F16>(__uint_as_float(rv[8 * gg + 4]), __uint_as_float(rv[8 * gg + 5]));
+              w4.w = gelu_pair<F16>(__uint_as_float(rv[8 * gg + 6]), __uint_as_float(rv[8 * gg + 7]));
+              *reinterpret_cast<uint4 *>(dst + (2 * pc + gg) * kCS) = w4;
+            }
           }
           fence_async_smem();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bars.hbfull[c % kBackHB]);
+          if (lane == 0) mbar_arrive(&bars.hbfull[c & 1]);
         }
-        tr(30 + j);
+        tr(30 + c);
         if (has_next) {
           const int gn = g + gridDim.x;
-          if (j < kStageParts) {   // next tile: out2 tile into the other operand buffer, a slice per chunk
-            stage_out2(gn, abuf + ((it + 1) & 1) * kTile144, j);
-          } else if (j == kStageParts) {
+          if (c == 0) {          // next tile: out2 tile into the other operand buffer
+            stage_out2(gn, abuf + ((it + 1) & 1) * kTile144, 0, 3);
+          } else if (c == 1) {
+            stage_out2(gn, abuf + ((it + 1) & 1) * kTile144, 3, kStageParts);
             // skip rows of the next tile into L2: this warp's 32 tokens x 36 channels, one lane per
             // (channel, 128-byte line) -- prefetches of the lanes of a warp are not coalesced
             const int bn = gn / tiles, tn0 = (gn % tiles) * kTM + q4 * 32;
@@ -521,39 +554,58 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const uint8_t *__re
                 if (cq + ch < kC) prefetch_l2(xn + (size_t)ch * T + (S2 ? (i & 1) * 32 : 0));
               }
             }
-          } else if (j == kStageParts + 1) {
+          } else if (c == 2) {
             publish_out2(it + 1);
           }
         }
       }
       // ---- y = u + s_m * (mlp + b_2) ----
       {
-        float *yp = y + ((size_t)b * kC + cq) * Tout + tt;
-        const int cl = c0 + kNChunk - 1;
-        (void)cl;
-        mbar_wait(&bars.yfull, it & 1);   // last W2 chunk of the tile: y accumulator complete
+        mbar_wait(&bars.yfull, it & 1);   // last W2 chunk of the tile: y accumulator complete, GELU tiles idle
         tc_fence_after();
         tr(50);
-        auto piece = [&](const float *v, int i0, int cnt) {
+        // the [channel][token] fp32 tile is assembled in the GELU tiles and leaves with ONE tensor-map TMA
+        // store (rows = (clip, channel), columns = tokens; the part of a ragged last tile beyond T' is
+        // clipped by the hardware).  Row pitches that are not a multiple of 16 bytes store directly.
+        const bool bulk = use_tma != 0;
+        float *stage = reinterpret_cast<float *>(hbuf);
+        float *yp = y + ((size_t)b * kC + cq) * Tout + tt;
+        {
+          float v[kCQ];
+          tmem_ld36(tcol(t_y, q4, cq), v);
+          const float4 *sm4 = reinterpret_cast<const float4 *>(V->sm + cq);
 #pragma unroll
-          for (int e = 0; e < cnt; ++e) {
-            const int i = i0 + e, n = cq + i;
-            if (n < kC && live) *yp = fmaf(V->sm[n], v[e] + V->b2[n], u[i]);
-            yp += Tout;
+          for (int q = 0; q < kCQ / 4; ++q) {
+            const float4 w = sm4[q];
+            const float ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = 4 * q + e, n = cq + i;
+              if (n < kC) {
+                const float val = fmaf(ww[e], v[i], u[i]);   // u already holds + s_m * b_2
+                if (bulk) stage[n * kTM + tok] = val;
+                else if (live) yp[(size_t)i * Tout] = val;
+              }
+            }
           }
-        };
-        float v[16];
-        tmem_ld16(tcol(t_y, q4, cq), v);
-        piece(v, 0, 16);
-        tmem_ld16(tcol(t_y, q4, cq + 16), v);
-        piece(v, 16, 16);
-        float v4[4];
-        tmem_ld4(tcol(t_y, q4, cq + 32), v4);
-        piece(v4, 32, 4);
+        }
+        tc_fence_before();   // ordered before this warp's next hbfull / lnfull arrival
+        tr(52);
+        if (bulk) {
+          fence_async_smem();
+          tr(53);
+          epi_bar_sync();
+          tr(54);
+          if (threadIdx.x == 0) {
+            tma_store_2d(&ymap, stage, t0, b * kC);
+            tma_store_commit();
+            y_store_pending = true;
+          }
+        }
       }
       tr(51);
-      tc_fence_before();   // ordered before this warp's next hbfull / lnfull arrival
     }
+    if (y_store_pending) tma_store_wait_all();   // writes done before the CTA exits
   }
   tc_fence_before();
   __syncthreads();

@@ -14,8 +14,10 @@
 // so a tile written once (one thread per row, 16-byte stores: bank-conflict free)
 // can feed a GEMM along either of its axes.
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace otp {
@@ -96,6 +98,54 @@ __device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gmem_sr
                ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+
+// ---------------------------------------------------------------- TMA (tensor-map tiles)
+// Host: descriptor of a row-major 2-D fp32 tensor (rows x cols, cols contiguous, row pitch = cols * 4 bytes,
+// which has to be a multiple of 16) accessed in (box_rows x box_cols) tiles, no swizzle: the tile lands in /
+// leaves from shared memory as a dense [box_rows][box_cols] array.  Out-of-range parts of a tile are not
+// written (stores) / zero-filled (loads), so ragged last tiles need no special path.  The driver entry point
+// is looked up through the runtime (no link-time dependency on libcuda).
+inline bool make_tensor_map_2d_f32(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols,
+                                   uint32_t box_rows, uint32_t box_cols) {
+  typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                               const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || !fn)
+      return false;
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  if ((cols * 4) % 16 != 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0 || box_rows > 256 || box_cols > 256) return false;
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstride[1] = {cols * 4};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// One thread: store the dense shared-memory tile at tensor coordinates (col0, row0) (UTMASTG); completion is
+// tracked by the thread's bulk async-group.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *smem_src, int col0, int row0) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(col0), "r"(row0)
+               : "memory");
+}
+// One thread: load the tile at (col0, row0) into shared memory (UTMALDG); completes on the mbarrier.
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int col0, int row0, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(col0), "r"(row0)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

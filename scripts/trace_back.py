@@ -55,4 +55,9 @@ k = min(len(t) for t in per_role) // 2
 origin = per_role[1][k][0][1]
 merged = sorted((c - origin, names[r], e) for r in range(3) for e, c in per_role[r][k])
 print(f"-- tile #{k}: cycle offset from the control warp's tile start, role:event")
-print("  ".join(f"{c}:{n}:{e}" for c, n, e in merged))
+print("  ".join(f"{c}:{n}:{e}" for c, n, e in merged if e not in (60, 61)))
+# control warp: cycles spent waiting for weight pieces (events 60 -> 61) per tile
+for tl in per_role[1][2:8]:
+    waits = [b[1] - a[1] for a, b in zip(tl, tl[1:]) if a[0] == 60 and b[0] == 61]
+    print("piece waits: n =", len(waits), "total", sum(waits), "max", max(waits) if waits else 0,
+          "over 200 cycles:", [w for w in waits if w > 200])
