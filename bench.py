@@ -48,6 +48,10 @@ def parse():
                     help="BASELINE configs[2]: a FIXED total of clips per step split over the ranks (strong scaling, "
                          "e.g. 512 -> 512/256/128/64 per GPU), each rank running its shard as forward calls of "
                          "--batch clips")
+    ap.add_argument("--train", action="store_true",
+                    help="BASELINE configs[3]: training step of the head (fwd + bwd + bucketed NCCL gradient "
+                         "all-reduce + clip + AdamW), --batch clips per GPU (default 64 in this mode)")
+    ap.add_argument("--train-micro", type=int, default=16, help="clips per micro-batch of a training step")
     ap.add_argument("--no-full-inference", action="store_true",
                     help="skip the BASELINE configs[1] leg (HRNet-W48 backbone + head, N=1 only)")
     ap.add_argument("--roofline-seconds", type=float, default=2.2,
@@ -516,10 +520,106 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """configs[3]: one training step per rank on its own clips, gradients all-reduced over NCCL.  The JSON
+    line states which parts of the step run on this library's kernels and which on library (ATen) ops --
+    see otpose_b200/model/train_ops.py."""
+    import torch
+    import torch.distributed as dist
+    from otpose_b200 import _lib
+    from otpose_b200.model import OTPose, default_cfg
+    from otpose_b200.model.loss import ST_OHKW_MSELoss
+    from otpose_b200.train import BucketedGradReducer, train_step
+    from otpose_b200.utils import synthetic as syn
+
+    rank, local_rank, world = dist_env()
+    lib = _lib.load()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    b = args.batch if args.batch != 32 else 64
+    model = OTPose(default_cfg((H, W)))
+    model.load_state_dict(syn.fill_state_dict({k: v.shape for k, v in model.state_dict().items()}, seed=2024))
+    model = model.to(dev).train()
+    params = [p for p in model.parameters() if p.requires_grad]
+    red = BucketedGradReducer(params, bucket_bytes=4 << 20)
+    opt = torch.optim.AdamW(params, lr=1e-4, fused=True)       # configs/Base_PoseTrack17.yaml:108-109
+    crit = ST_OHKW_MSELoss(use_target_weight=True)
+    rough = syn.synth_rough_heatmaps(b, J, H, W, seed=shard_seed(1234, rank)).to(dev)
+    margin = syn.synth_margin(b, seed=shard_seed(1236, rank)).to(dev)
+    target = syn.synth_rough_heatmaps(b, J, H, W, frames=1, seed=shard_seed(1238, rank)).to(dev)
+    tw = torch.ones(b, J, 1, device=dev)
+    comm_ms = []
+
+    def step():
+        return train_step(model, crit, opt, red, rough, margin, target, tw, clip_grad_l2norm=1.0,
+                          micro_batch=args.train_micro)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    wall0 = time.time()
+    launches0 = lib.otp_launch_count()
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss, norm = step()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms = dist_max(e0.elapsed_time(e1), dev)
+    launches = lib.otp_launch_count() - launches0
+    # the all-reduce alone (same buckets, nothing to overlap with): its share of the step if it were exposed
+    if world > 1:
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(10):
+            red.zero_grad()
+            red.finish()
+        c1.record()
+        torch.cuda.synchronize()
+        comm_ms.append(c0.elapsed_time(c1) / 10)
+    wall1 = time.time()
+    clocks = sampler.stop(wall0, wall1) if sampler else None
+    if rank == 0:
+        line = {"metric": "temporal_head_train_person_clips_per_s", "value": b * world * args.steps / (ms * 1e-3),
+                "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"OTPose temporal-head training step (BASELINE configs[3]): fwd + bwd + bucketed "
+                                       f"NCCL gradient all-reduce + global-norm clip + AdamW, {b} clips/GPU in "
+                                       f"micro-batches of {args.train_micro}, {FRAMES} frames, {H}x{W}, {J} joints, "
+                                       f"random-init weights, backbone frozen (FREEZE_HRNET_WEIGHTS)",
+                           "native": "offset / mask convs and modulated DCN, forward and backward (C ABI kernels)",
+                           "library": "TransformerBlocks, RSB chains, pyramid 1x1 convs, prologue, loss: ATen ops "
+                                      "under autograd (otpose_b200/model/train_ops.py)",
+                           "clips_per_gpu": b, "heatmap": [H, W], "joints": J},
+                "clocks": clocks, "gpu_launches": int(launches),
+                "loss": float(loss), "grad_norm": float(norm),
+                "allreduce": {"buckets": red.num_buckets, "bytes": int(red.flat.numel() * 4), "ranks": world,
+                              "exposed_ms": comm_ms[0] if comm_ms else 0.0,
+                              "share_of_step_if_exposed": (comm_ms[0] / (ms / args.steps)) if comm_ms else 0.0,
+                              "overlap": "buckets launched from autograd hooks under the last micro-batch's backward"}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.train:
+        run_train(args)
     else:
         run_b200(args)
 

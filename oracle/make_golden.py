@@ -174,6 +174,23 @@ def main():
     img = torch.from_numpy(np.random.default_rng(31).standard_normal((1, 3, 64, 64)).astype(np.float32))
     save("hrnet_w48_64x64", x=img, seed=2024, out=net(img))
 
+    # ---- ST_OHKW_MSELoss (reference model/loss.py, imported as-is) -----------
+    from model.loss import ST_OHKW_MSELoss as RefLoss
+    r = np.random.default_rng(41)
+    lb, lj, lh, lw = 3, 17, 12, 10
+    out_s = torch.from_numpy(r.random((lb, lj, lh, lw)).astype(np.float32)).requires_grad_(True)
+    out_t = torch.from_numpy(r.random((lb, lj, lh, lw)).astype(np.float32))
+    gt = r.random((lb, lj, lh, lw)).astype(np.float32) * 0.9
+    gt[:, ::3] = gt[:, ::3] / gt[:, ::3].max(axis=(0, 2, 3), keepdims=True)     # every third joint peaks at exactly 1
+    gt = torch.from_numpy(gt)
+    tw = torch.from_numpy((r.random((lb, lj, 1)) > 0.2).astype(np.float32))
+    with torch.enable_grad():
+        res = RefLoss(use_target_weight=True)(out_s, out_t, gt, tw)
+        grad = torch.autograd.grad(res["final_loss"], out_s)[0]
+    save("loss_st_ohkw", output_s=out_s.detach(), output_t=out_t, target=gt, target_weight=tw,
+         ohkm_loss_s=res["ohkm_loss_s"].detach(), mse_loss_s=res["mse_loss_s"].detach(),
+         final_loss=res["final_loss"].detach(), grad_output_s=grad)
+
     # ---- get_final_preds / get_max_preds (reference numpy code + cv2) --------
     hm = syn.synth_rough_heatmaps(3, 17, 24, 18, frames=1, seed=77).numpy()
     hm[0, 0] = 0.0                      # all-zero map: maxval <= 0 -> coords zeroed

@@ -76,8 +76,10 @@ class ConvTransformer(nn.Module):
         return outs
 
     def forward(self, x):
-        if self.training:
-            raise NotImplementedError("CUDA ConvTransformer implements eval-mode forward; call .eval()")
+        if self.training:      # differentiable path (train_ops: library ops under autograd)
+            from . import train_ops
+            _lib.require_cuda(x)
+            return train_ops.conv_transformer(self, x)
         _lib.require_cuda(x)
         b, c, h, w = x.shape
         t = h * w

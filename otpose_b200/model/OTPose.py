@@ -301,6 +301,12 @@ class OTPose(nn.Module):
         7-tuple.  ``squeezed`` is returned as a stride-0 expand of the (B,1,H,W) plane
         (same values as the reference's J-fold stack).  With ``cuda_graph=True`` the launches are
         replayed from a captured CUDA graph (see ``_forward_head_graphed``)."""
+        if self.training:
+            # differentiable path (model/train_ops.py): native DCN + offset / mask conv forward and backward,
+            # library ops under autograd for the blocks / RSB chains -- see the status note there
+            from . import train_ops
+            _lib.require_cuda(rough_heatmaps)
+            return train_ops.head_forward_train(self, rough_heatmaps, margin)
         if (self.cuda_graph and _debug is None and not self.training and rough_heatmaps.is_cuda
                 and rough_heatmaps.shape[0] > 0 and not torch.cuda.is_current_stream_capturing()):
             return self._forward_head_graphed(rough_heatmaps, margin)

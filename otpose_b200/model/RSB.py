@@ -72,8 +72,10 @@ class conv_bn_relu(nn.Module):
                                   _lib.stream_ptr(wt.device)), "otp_conv2d")
 
     def forward(self, x):
-        if self.training:
-            raise NotImplementedError("CUDA conv_bn_relu implements eval-mode forward; call .eval()")
+        if self.training:      # differentiable path (train_ops: library ops under autograd, BN batch statistics)
+            from . import train_ops
+            _lib.require_cuda(x)
+            return train_ops.conv_bn_relu(self, x)
         _lib.require_cuda(x)
         b, c, h, w = x.shape
         y = torch.empty((b, self.conv.out_channels, h, w), dtype=torch.float32, device=x.device)
@@ -102,7 +104,9 @@ class RSB_BLOCK(nn.Module):
         buffer holding the ten branch outputs; the concat (out_1_1, out_2_2, out_3_3,
         out_4_4) is assembled by writing those four convs into a (B,4bc,H,W) buffer."""
         if self.training:
-            raise NotImplementedError("CUDA RSB_BLOCK implements eval-mode forward; call .eval()")
+            from . import train_ops
+            _lib.require_cuda(x)
+            return train_ops.rsb_block(self, x)
         _lib.require_cuda(x)
         b, cin, h, w = x.shape
         p = h * w

@@ -166,9 +166,13 @@ class TransformerBlock(nn.Module):
         return t if self.stride == 1 else (t - 1) // 2 + 1
 
     def forward(self, x, pos_embd=None, precision="fp32"):
-        """x (B, C, T) fp32 CUDA -> (B, C, T') (reference model/blocks.py:264-279, eval mode)."""
+        """x (B, C, T) fp32 CUDA -> (B, C, T') (reference model/blocks.py:264-279).  Eval mode: the fused
+        CUDA passes.  Training mode: the differentiable library-op composition of ``train_ops`` (dropout,
+        drop-path; see that module's status note)."""
         if self.training:
-            raise NotImplementedError("CUDA TransformerBlock implements eval-mode forward; call .eval()")
+            from . import train_ops
+            _lib.require_cuda(x)          # same contract as the kernels: no CPU path, in either mode
+            return train_ops.transformer_block(self, x)
         if pos_embd is not None:
             raise NotImplementedError("pos_embd argument is unused by ConvTransformer")
         _lib.require_cuda(x)

@@ -106,7 +106,7 @@ def test_cpu_tensors_are_rejected_like_the_reference():
     blk = ConvTransformer(17, 17, 1, 3, 64, arch=(0, 1, 0), h=8).eval()
     with pytest.raises(NotImplementedError):
         blk(torch.zeros(1, 17, 8, 8))
-    with pytest.raises(NotImplementedError):   # training-mode semantics are not built
+    with pytest.raises(NotImplementedError):   # the training path keeps the contract: CUDA tensors only
         ConvTransformer(17, 17, 1, 3, 64, arch=(0, 1, 0), h=8).train()(torch.zeros(1, 17, 8, 8))
     head = OTPose(default_cfg((8, 8))).eval()
     with pytest.raises(NotImplementedError):   # the feature hand-off boundary keeps the same contract
@@ -148,3 +148,20 @@ def test_hrnet_drop_in_matches_reference_golden():
     assert out.shape == ref.shape and feats.shape == (1, 48, 16, 16)
     assert (out - ref).abs().max() / scale < 1e-6
     assert (folded - ref).abs().max() / scale < 1e-5
+
+
+def test_device_side_loss_matches_reference_golden():
+    """ST_OHKW_MSELoss without the per-joint host synchronisation equals the reference's
+    loop (fixture from the reference's own model/loss.py: values and the gradient wrt the student maps)."""
+    import numpy as np
+    from otpose_b200.model.loss import ST_OHKW_MSELoss
+    g = np.load(os.path.join(ROOT, "tests", "golden", "loss_st_ohkw.npz"))
+    s = torch.from_numpy(g["output_s"]).requires_grad_(True)
+    res = ST_OHKW_MSELoss(use_target_weight=True)(s, torch.from_numpy(g["output_t"]), torch.from_numpy(g["target"]),
+                                                  torch.from_numpy(g["target_weight"]))
+    for k in ("ohkm_loss_s", "mse_loss_s", "final_loss"):
+        assert abs(float(res[k]) - float(g[k])) <= 1e-6 * max(1.0, abs(float(g[k]))), k
+    grad = torch.autograd.grad(res["final_loss"], s)[0]
+    assert (grad - torch.from_numpy(g["grad_output_s"])).abs().max() < 1e-7
+    with pytest.raises(NotImplementedError):
+        ST_OHKW_MSELoss(use_target_weight=False)
