@@ -36,7 +36,9 @@ constexpr int kGramLd = kKP;                  // row stride (floats) of a partia
 constexpr int kGramRows = kC + 1;             // 137: channels + the ones row
 struct Front1Vec {
   float ln1w[kC], ln1b[kC];
-  float4 dw[3][kC];          // depthwise taps of q, k, v
+  float4 dw[3][kC];          // depthwise taps of q, k, v (fp32: the stride-2 blocks, whose centre tap is fp32)
+  uint4 dwh[3][kKP / 8][3];  // the same taps as IEEE-half pairs, [branch][8-channel group][tap]: the stride-1
+                             // blocks run the depthwise conv in packed half2 on the half LN1 tile
   float part[2][4][3][kTM];  // [parity of the pass][mean | M2 or sum | sumsq (| odd input: mean | M2)][third][token]
 };
 struct Front1Bars {
@@ -88,6 +90,11 @@ tc_front1_kernel(BlockPack P, const float *__restrict__ x, float *__restrict__ g
     V->dw[0][c] = make_float4(P.dwq[3 * c], P.dwq[3 * c + 1], P.dwq[3 * c + 2], 0.f);
     V->dw[1][c] = make_float4(P.dwk[3 * c], P.dwk[3 * c + 1], P.dwk[3 * c + 2], 0.f);
     V->dw[2][c] = make_float4(P.dwv[3 * c], P.dwv[3 * c + 1], P.dwv[3 * c + 2], 0.f);
+  }
+  for (int e = threadIdx.x; e < 3 * kKP * 3; e += kFrThreads) {   // (branch, channel, tap) -> half
+    const int m = e / (kKP * 3), c = (e / 3) % kKP, tap = e % 3;
+    const float *src = m == 0 ? P.dwq : (m == 1 ? P.dwk : P.dwv);
+    reinterpret_cast<__half *>(&V->dwh[m][c >> 3][tap])[c & 7] = __float2half_rn(c < kC ? src[3 * c + tap] : 0.f);
   }
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -302,22 +309,41 @@ tc_front1_kernel(BlockPack P, const float *__restrict__ x, float *__restrict__ g
 #pragma unroll
         for (int g = 0; g < 6; ++g) {
           if (g * 8 < nq) {
-            float l8[8], c8[8], r8[8];
-            unpack8(*reinterpret_cast<const uint4 *>(lrow + g * 16), l8);
-            if (S2) {
+            if constexpr (!S2) {
+              // stride 1: all three taps are rows of the half LN1 tile -> the conv runs in packed half2 (3
+              // HFMA2-class instructions per channel PAIR instead of 6 conversions + 6 fp32 FMAs); the
+              // statistics and the normalisation stay fp32
+              const uint4 lq = *reinterpret_cast<const uint4 *>(lrow + g * 16);
+              const uint4 cq4 = *reinterpret_cast<const uint4 *>(hrow + g * 16);
+              const uint4 rq = *reinterpret_cast<const uint4 *>(rrow + g * 16);
+              const uint4 *wt = V->dwh[m][(c_lo >> 3) + g];
+              const uint4 wl = wt[0], wc = wt[1], wr = wt[2];
+              const __half2 *l2 = reinterpret_cast<const __half2 *>(&lq), *c2 = reinterpret_cast<const __half2 *>(&cq4),
+                            *r2 = reinterpret_cast<const __half2 *>(&rq), *wl2 = reinterpret_cast<const __half2 *>(&wl),
+                            *wc2 = reinterpret_cast<const __half2 *>(&wc), *wr2 = reinterpret_cast<const __half2 *>(&wr);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const __half2 hv = __hfma2(wr2[q], r2[q], __hfma2(wc2[q], c2[q], __hmul2(wl2[q], l2[q])));
+                const float2 f = __half22float2(hv);
+                d[g * 8 + 2 * q] = f.x;
+                d[g * 8 + 2 * q + 1] = f.y;
+                s += f.x + f.y;
+                ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss));
+              }
+            } else {
+              float l8[8], c8[8], r8[8];
+              unpack8(*reinterpret_cast<const uint4 *>(lrow + g * 16), l8);
 #pragma unroll
               for (int e = 0; e < 8; ++e) c8[e] = xr[g * 8 + e];
-            } else {
-              unpack8(*reinterpret_cast<const uint4 *>(hrow + g * 16), c8);
-            }
-            unpack8(*reinterpret_cast<const uint4 *>(rrow + g * 16), r8);
+              unpack8(*reinterpret_cast<const uint4 *>(rrow + g * 16), r8);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float4 w = V->dw[m][c_lo + g * 8 + e];
-              const float v = fmaf(w.z, r8[e], fmaf(w.y, c8[e], w.x * l8[e]));
-              d[g * 8 + e] = v;
-              s += v;
-              ss = fmaf(v, v, ss);
+              for (int e = 0; e < 8; ++e) {
+                const float4 w = V->dw[m][c_lo + g * 8 + e];
+                const float v = fmaf(w.z, r8[e], fmaf(w.y, c8[e], w.x * l8[e]));
+                d[g * 8 + e] = v;
+                s += v;
+                ss = fmaf(v, v, ss);
+              }
             }
           } else {
 #pragma unroll
