@@ -455,12 +455,16 @@ int forward_tc_t(const void *packed_fp32, const void *packed_tc, const float *x,
   }
   {
     LaunchScope ls(K_TC_FRONT, st);
+    // x as a 2-D tensor [(clip, channel)][token] read in [136][128] tiles by TMA (stride-1 blocks)
+    alignas(64) CUtensorMap xmap;
+    memset(&xmap, 0, sizeof(xmap));
+    const int x_tma = (stride == 1 && make_tensor_map_2d_f32(&xmap, x, (uint64_t)b * kC, (uint64_t)t, kC, kTM)) ? 1 : 0;
     if (stride == 1)
       tc_front1_kernel<F16, false><<<dim3(W.nchunk, b), kFrThreads, kFront1Smem, st>>>(
-          P, x, gram, vn, t, W.tout, W.tiles, W.tiles_per_chunk, W.nchunk, g_trace_on);
+          P, x, xmap, x_tma, gram, vn, t, W.tout, W.tiles, W.tiles_per_chunk, W.nchunk, g_trace_on);
     else
       tc_front1_kernel<F16, true><<<dim3(W.nchunk, b), kFrThreads, kFront1Smem, st>>>(
-          P, x, gram, vn, t, W.tout, W.tiles, W.tiles_per_chunk, W.nchunk, g_trace_on);
+          P, x, xmap, 0, gram, vn, t, W.tout, W.tiles, W.tiles_per_chunk, W.nchunk, g_trace_on);
   }
   {
     // S = Wq~ G~ Wk~^T in fp32 (8 column blocks per clip), then softmax + W_eff fold

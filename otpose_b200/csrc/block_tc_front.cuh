@@ -42,12 +42,14 @@ struct Front1Vec {
   float part[2][4][3][kTM];  // [parity of the pass][mean | M2 or sum | sumsq (| odd input: mean | M2)][third][token]
 };
 struct Front1Bars {
-  uint64_t abfull[2];        // compute -> MMA: a~ and c~ tiles of buffer s staged (12 warp arrivals)
-  uint64_t gdone[2];         // Gram UMMAs reading buffer s done: buffer reusable
+  uint64_t abfull;           // compute -> MMA: a~ and c~ tiles staged (12 warp arrivals)
+  uint64_t gdone;            // Gram UMMAs of the tile done: a~ / c~ tiles reusable
+  uint64_t xfull;            // TMA arrival of the fp32 x tile (stride-1 blocks with a 16-byte row pitch)
   uint64_t halo_full[2];     // halo rows of tile n staged in halo[n & 1]
   uint64_t adone;            // compute warps are done reading the LN1 tile / halo rows (12 warp arrivals)
 };
-constexpr size_t kFront1Smem = (size_t)kTM * kHsRow + 4 * kHsRow + 4 * kTile144 + sizeof(Front1Vec);
+constexpr uint32_t kXTile = kC * kTM * 4;     // 69632: fp32 [136 channels][128 tokens] x tile (TMA box)
+constexpr size_t kFront1Smem = (size_t)kXTile + 2 * kTile144 + (size_t)kTM * kHsRow + 4 * kHsRow + sizeof(Front1Vec);
 static_assert(kFront1Smem + 1024 <= 227 * 1024, "tc_front1 shared memory");
 
 __device__ __forceinline__ void fr_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kFrComp) : "memory"); }
@@ -69,12 +71,13 @@ __device__ __forceinline__ void unpack8(const uint4 &p, float (&f)[8]) {
 // 14 warps: the busiest scheduler partition holds 4 of them, i.e. 16384 / 4 / 32 = 128 registers per thread
 template <bool F16, bool S2>
 __global__ void __launch_bounds__(kFrThreads, 1)
-tc_front1_kernel(BlockPack P, const float *__restrict__ x, float *__restrict__ gram_part,
-                 uint8_t *__restrict__ vn_img, int T, int Tout, int tiles, int tiles_per_chunk, int nchunk,
-                 int trace) {
+tc_front1_kernel(BlockPack P, const float *__restrict__ x, const __grid_constant__ CUtensorMap xmap, int use_tma,
+                 float *__restrict__ gram_part, uint8_t *__restrict__ vn_img, int T, int Tout, int tiles,
+                 int tiles_per_chunk, int nchunk, int trace) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t *ab = smem;                          // [2 buffers][a~ tile | c~ tile], [token][channel] 16-bit
-  uint8_t *hs = ab + 4 * kTile144;             // [128][136] halves: LN1(x) of the tile's tokens
+  float *xs = reinterpret_cast<float *>(smem); // fp32 x tile [136][128], filled by one tensor-map TMA load per tile
+  uint8_t *ab = smem + kXTile;                 // [a~ tile | c~ tile], [token][channel] 16-bit
+  uint8_t *hs = ab + 2 * kTile144;             // [128][136] halves: LN1(x) of the tile's tokens
   uint8_t *halo = hs + kTM * kHsRow;           // [2][2][136] halves: LN1(x) of tokens t0-1 / t0+128
   Front1Vec *V = reinterpret_cast<Front1Vec *>(halo + 4 * kHsRow);
   __shared__ Front1Bars bars;
@@ -97,12 +100,11 @@ tc_front1_kernel(BlockPack P, const float *__restrict__ x, float *__restrict__ g
     reinterpret_cast<__half *>(&V->dwh[m][c >> 3][tap])[c & 7] = __float2half_rn(c < kC ? src[3 * c + tap] : 0.f);
   }
   if (threadIdx.x == 0) {
+    mbar_init(&bars.abfull, kFrComp / 32);
+    mbar_init(&bars.gdone, 1);
+    mbar_init(&bars.xfull, 1);
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars.abfull[i], kFrComp / 32);
-      mbar_init(&bars.gdone[i], 1);
-      mbar_init(&bars.halo_full[i], 1);
-    }
+    for (int i = 0; i < 2; ++i) mbar_init(&bars.halo_full[i], 1);
     mbar_init(&bars.adone, kFrComp / 32);
     fence_mbar_init();
   }
@@ -121,8 +123,8 @@ tc_front1_kernel(BlockPack P, const float *__restrict__ x, float *__restrict__ g
     const uint32_t ab0 = smem_u32(ab);
     uint32_t n = 0;
     for (int tile = tile_begin; tile < tile_end; ++tile, ++n) {
-      const uint32_t a_s = ab0 + (n & 1) * 2 * kTile144, c_s = a_s + kTile144;
-      mbar_wait(&bars.abfull[n & 1], (n >> 1) & 1);
+      const uint32_t a_s = ab0, c_s = a_s + kTile144;
+      mbar_wait(&bars.abfull, n & 1);
       tc_fence_after();
 #pragma unroll
       for (int s = 0; s < kTM / 16; ++s) {
@@ -132,7 +134,7 @@ tc_front1_kernel(BlockPack P, const float *__restrict__ x, float *__restrict__ g
         umma_elect(t_g1, make_desc(a_s + ko + 2 * kCS, kRS144, kCS), make_desc(c_s + ko, kRS144, kCS), idesc_gram,
                    !(n == 0 && s == 0));
       }
-      commit_elect(&bars.gdone[n & 1]);
+      commit_elect(&bars.gdone);
     }
   } else if (warp == kFrComp / 32 + 1) {
     // =============================================================== HALO
@@ -188,7 +190,28 @@ tc_front1_kernel(BlockPack P, const float *__restrict__ x, float *__restrict__ g
         p += T;
       }
     };
-    if (!S2 && tile_begin < tile_end) load_x(tile_begin);
+    // stride-1 blocks whose rows are 16-byte aligned: the tile's x arrives as ONE tensor-map TMA load
+    // (cp.async.bulk.tensor.2d, UTMALDG) into shared memory while the previous tile is being processed, and
+    // every thread picks its 48 values up from there -- 48 strided global loads per thread kept the compute
+    // warps blocked for ~3 k cycles per tile while the SM's load queue drained
+    const bool tma_x = !S2 && use_tma != 0;
+    auto issue_x_tma = [&](int tile) {   // one thread
+      mbar_expect_tx(&bars.xfull, kXTile);
+      tma_load_2d(xs, &xmap, tile * kTM, b * kC, &bars.xfull);
+    };
+    auto take_x = [&](uint32_t nn) {     // xs -> registers
+      mbar_wait(&bars.xfull, nn & 1);
+      const float *p = xs + c_lo * kTM + tok;
+#pragma unroll
+      for (int i = 0; i < 48; ++i) xr[i] = i < nq ? p[i * kTM] : 0.f;
+    };
+    if (tile_begin < tile_end) {
+      if (tma_x) {
+        if (threadIdx.x == 0) issue_x_tma(tile_begin);
+      } else if (!S2) {
+        load_x(tile_begin);
+      }
+    }
     uint32_t n = 0, pp = 0;
     const uint8_t *hrow = hs + tok * kHsRow + c_lo * 2;
     // optional phase trace (build with -DOTP_FRONT_TRACE, then otp_debug_trace / scripts/trace_front.py):
@@ -206,9 +229,10 @@ tc_front1_kernel(BlockPack P, const float *__restrict__ x, float *__restrict__ g
       const bool live = tok < nvalid;                             // output token (and its even input) exists
       const bool live_o = S2 && 2 * (t0 + tok) + 1 < T;           // its odd input exists
       uint8_t *vn_tile = vn_img + ((size_t)b * tiles + tile) * kTile144;
-      uint8_t *a_tile = ab + (n & 1) * 2 * kTile144, *c_tile = a_tile + kTile144;
+      uint8_t *a_tile = ab, *c_tile = a_tile + kTile144;
       tr(0);
       if (S2) load_x(tile);
+      if (tma_x) take_x(n);
       // ---- LN1 over the token's 136 channels: per-thread (mean, M2), parallel-variance combine ----
       {
         float s = 0.f;
@@ -241,6 +265,10 @@ tc_front1_kernel(BlockPack P, const float *__restrict__ x, float *__restrict__ g
       tr(1);
       fr_bar_sync();
       tr(2);
+      if (tma_x && threadIdx.x == 0 && tile + 1 < tile_end) {   // every thread has its x in registers: refill
+        fence_async_smem();
+        issue_x_tma(tile + 1);
+      }
       if (S2) {   // odd input: LN1 -> 16-bit shared row; the even input is normalised in place below (xr := h)
         const float m0 = V->part[pp][2][0][tok], m1 = V->part[pp][2][1][tok], m2 = V->part[pp][2][2][tok];
         const float mu = (48.f * (m0 + m1) + 40.f * m2) * (1.0f / kC);
@@ -361,8 +389,9 @@ tc_front1_kernel(BlockPack P, const float *__restrict__ x, float *__restrict__ g
         const float rstd = 1.0f / sqrtf(var + 1e-5f);
         const float nmr = -mean * rstd;   // (d - mean) * rstd as one FMA
         pp ^= 1;
-        // the Gram UMMAs of tile n-2 still read this buffer's a~ / c~ tiles: wait before overwriting them
-        if (m == 0 && n >= 2) mbar_wait(&bars.gdone[n & 1], ((n >> 1) - 1) & 1);
+        // the Gram UMMAs of the previous tile still read the a~ / c~ tiles (they were issued a whole LN1 phase
+        // ago): wait before overwriting them
+        if (m == 0 && n >= 1) mbar_wait(&bars.gdone, (n - 1) & 1);
         tr(30 + m);
         uint8_t *dst = (m == 0 ? a_tile : (m == 1 ? c_tile : vn_tile)) + cm_offset(tok, c_lo, kRS144, kCS);
 #pragma unroll
@@ -383,17 +412,17 @@ tc_front1_kernel(BlockPack P, const float *__restrict__ x, float *__restrict__ g
       fence_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars.abfull[n & 1]);
+      if (lane == 0) mbar_arrive(&bars.abfull);
       // next tile's x: issued behind the tile's only proxy fence (fence.proxy.async waits for the thread's
       // pending loads), in flight during the v pass
-      if (!S2 && tile + 1 < tile_end) load_x(tile + 1);
+      if (!S2 && !tma_x && tile + 1 < tile_end) load_x(tile + 1);
       pass(std::integral_constant<int, 2>{});
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.adone);
     }
     // ---- flush the partial G~: TMEM lane == a~ channel (row), column == c~ channel ----
     if (n > 0) {
-      mbar_wait(&bars.gdone[(n - 1) & 1], ((n - 1) >> 1) & 1);   // commits complete in order: every tile is in
+      mbar_wait(&bars.gdone, (n - 1) & 1);   // commits complete in order: every tile is in
       tc_fence_after();
       float *gp = gram_part + (size_t)(b * nchunk + chunk) * kKP * kGramLd;
 #pragma unroll 1
