@@ -365,6 +365,7 @@ def run_b200(args):
     model = OTPose(default_cfg((H, W)), precision=precision, cuda_graph=not args.no_cuda_graph)
     model.load_state_dict(syn.fill_state_dict({k: v.shape for k, v in model.state_dict().items()}, seed=2024))
     model = model.to(dev).eval()
+    model.graph_clone_outputs = False   # the step consumes the outputs at once (final_preds): no defensive copies
     # every forward call of a step has its own synthetic clips (seeded per rank and call), resident on the
     # device for `value`, in pinned host memory for `e2e`
     hosts, resident, cs = [], [], []

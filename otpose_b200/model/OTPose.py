@@ -75,6 +75,8 @@ class OTPose(nn.Module):
         self.temporal_encoding_dim = self.patch_dim * self.num_frames
         self.precision = precision
         self.cuda_graph = bool(cuda_graph)   # opt-in: replay forward_head from a captured CUDA graph
+        self.graph_clone_outputs = True      # graph mode returns copies; False = the graph's static buffers, which
+                                             # the NEXT forward_head call overwrites (zero-copy serving loops)
         self._graphs = {}
         self._side_streams = {}
         self._pyramid_cache = {}
@@ -143,16 +145,16 @@ class OTPose(nn.Module):
         """16-bit operand images of offsets_list[i] / masks_list[i] for the fused tensor-core
         kernel; rebuilt when either weight changed."""
         wo, wm = self.offsets_list[i][0].weight, self.masks_list[i][0].weight
-        key = (wo.data_ptr(), wo._version, wm.data_ptr(), wm._version)
+        key = (id(wo), wo.data_ptr(), wo._version, id(wm), wm.data_ptr(), wm._version)
         cache = self.__dict__.setdefault("_om_cache", {})
-        if cache.get(i, (None, None))[0] != key:
+        if cache.get(i, (None,))[0] != key:
             lib = _lib.load()
             buf = torch.empty(lib.otp_offset_mask_pack_bytes(), dtype=torch.uint8, device=wo.device)
             with torch.cuda.device(wo.device):
                 _lib.check(lib.otp_offset_mask_pack(_lib.dptr(wo.detach()), _lib.dptr(wm.detach()), self.num_joints,
                                                     wo.shape[1], buf.data_ptr(), buf.numel(),
                                                     _lib.stream_ptr(wo.device)), "otp_offset_mask_pack")
-            cache[i] = (key, buf)
+            cache[i] = (key, buf, (wo, wm))          # the sources stay alive with the entry
         return cache[i][1]
 
     # ------------------------------------------------------------------
@@ -167,7 +169,7 @@ class OTPose(nn.Module):
 
     def _pyramid_packed(self, i, fl, prec):
         """16-bit operand image of final_layer{i+1}.weight (cached; rebuilt when the parameter changes)."""
-        key = (fl.weight.data_ptr(), fl.weight._version, prec)
+        key = (id(fl.weight), fl.weight.data_ptr(), fl.weight._version, prec)
         ent = self._pyramid_cache.get(i)
         if ent is None or ent[0] != key:
             lib = _lib.load()
@@ -177,7 +179,7 @@ class OTPose(nn.Module):
             _lib.check(lib.otp_pyramid_conv1x1_tc_pack(_lib.dptr(fl.weight.detach().view(j, c3).contiguous()), c3 // 3, j,
                                                        prec, buf.data_ptr(), nbytes,
                                                        _lib.stream_ptr(fl.weight.device)), "otp_pyramid_conv1x1_tc_pack")
-            ent = self._pyramid_cache[i] = (key, buf)
+            ent = self._pyramid_cache[i] = (key, buf, fl.weight)
         return ent[1]
 
     # ------------------------------------------------------------------ a0: HRNet.final_layer boundary
@@ -293,6 +295,10 @@ class OTPose(nn.Module):
         s_rough.copy_(rough, non_blocking=True)
         s_margin.copy_(margin, non_blocking=True)
         graph.replay()
+        if self.graph_clone_outputs:
+            # callers may keep results across steps (a validation loop accumulating predictions): hand out copies
+            # (`squeezed`, a stride-0 expand of one plane, is materialised as the reference's J-fold stack)
+            return (outs[0].clone(), rough_heatmaps) + tuple(o.clone() for o in outs[2:])
         return (outs[0], rough_heatmaps) + tuple(outs[2:])
 
     def forward_head(self, rough_heatmaps, margin, _debug=None):

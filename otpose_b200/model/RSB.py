@@ -34,7 +34,7 @@ class conv_bn_relu(nn.Module):
         """(weight, bias) with the eval-mode BatchNorm affine folded in (RSB.py:120-131)."""
         ps = [self.conv.weight, self.conv.bias, self.bn.weight, self.bn.bias, self.bn.running_mean,
               self.bn.running_var]
-        key = tuple((p.data_ptr(), p._version) for p in ps)
+        key = tuple((id(p), p.data_ptr(), p._version) for p in ps)   # the entry below keeps `ps` alive
         if self._folded is None or key != self._folded_key:
             with torch.no_grad():
                 w, b = self.conv.weight.detach().float(), self.conv.bias.detach().float()
@@ -44,6 +44,7 @@ class conv_bn_relu(nn.Module):
                     b = (b - self.bn.running_mean) * g + self.bn.bias.detach()
                 self._folded = (w.contiguous(), b.contiguous())
             self._folded_key = key
+            self._folded_src = ps
         return self._folded
 
     def run(self, x, x_bs, out, out_bs, b, h, w, x_add=None, x_add_bs=0, residual=None, residual_bs=0,

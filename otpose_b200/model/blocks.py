@@ -144,7 +144,9 @@ class TransformerBlock(nn.Module):
     def packed_weights(self) -> torch.Tensor:
         """Packed device copy of this block's weights, rebuilt when any parameter changed."""
         plist = self._param_list()
-        key = tuple((p.data_ptr(), p._version) if p is not None else None for _, p in plist)
+        # (address, version) per parameter; the cache entry keeps the source tensors alive, so an address
+        # cannot be handed to a replacement Parameter while the entry exists (init_weights re-binds parameters)
+        key = tuple((id(p), p.data_ptr(), p._version) if p is not None else None for _, p in plist)
         if self._packed is None or key != self._packed_key:
             lib = _lib.load()
             dev = self.ln1.weight.device
@@ -160,6 +162,7 @@ class TransformerBlock(nn.Module):
                 _lib.check(lib.otp_block_pack(C.byref(params), self.n_embd, self.n_head, buf.data_ptr(),
                                               nbytes, _lib.stream_ptr(dev)), "otp_block_pack")
             self._packed, self._packed_key = buf, key
+            self._packed_src = [p for _, p in plist]
         return self._packed
 
     def out_len(self, t: int) -> int:

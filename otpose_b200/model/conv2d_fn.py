@@ -22,11 +22,13 @@ _CIN_CHUNK = 48   # otp_conv2d keeps the (Cin*k*k, 16) weight tile of a CTA in s
 def _launch_conv(x, weight, bias, dilation):
     """y = conv(x) + bias.  Wide inputs (the grad_input conv of a 32 -> 306 layer has Cin = 306) are run as a
     chain over input-channel chunks, each launch adding the previous partial through the kernel's fused
-    residual input (same thread reads and writes an element, so the chain runs in place)."""
+    residual input; the partials ping-pong between two buffers (the kernel reads its residual through the
+    read-only path and declares it __restrict__, so a launch never reads what it writes)."""
     lib = _lib.load()
     b, cin, h, w = x.shape
     cout, k = weight.shape[0], weight.shape[2]
-    y = torch.empty((b, cout, h, w), dtype=torch.float32, device=x.device)
+    bufs = [torch.empty((b, cout, h, w), dtype=torch.float32, device=x.device), None]
+    cur = 0
     if b:
         p = h * w
         with torch.cuda.device(x.device):
@@ -34,11 +36,18 @@ def _launch_conv(x, weight, bias, dilation):
             for c0 in range(0, cin, _CIN_CHUNK):
                 c1 = min(cin, c0 + _CIN_CHUNK)
                 wc = weight if (c0 == 0 and c1 == cin) else weight[:, c0:c1].contiguous()
+                if c0 == 0:
+                    res, out = None, bufs[0]
+                else:                      # the partial so far is the residual; the sum goes to the other buffer
+                    if bufs[1 - cur] is None:
+                        bufs[1 - cur] = torch.empty_like(bufs[cur])
+                    res, out = bufs[cur], bufs[1 - cur]
+                    cur = 1 - cur
                 _lib.check(lib.otp_conv2d(x.data_ptr() + 4 * c0 * p, cin * p, None, 0, _lib.dptr(wc),
                                           _lib.dptr(bias, allow_none=True) if c0 == 0 else None,
-                                          y.data_ptr() if c0 else None, cout * p, y.data_ptr(), cout * p, b, c1 - c0,
-                                          h, w, cout, k, dilation, 0, st), "otp_conv2d")
-    return y
+                                          res.data_ptr() if res is not None else None, cout * p, out.data_ptr(),
+                                          cout * p, b, c1 - c0, h, w, cout, k, dilation, 0, st), "otp_conv2d")
+    return bufs[cur]
 
 
 class Conv2dFunction(torch.autograd.Function):
