@@ -600,8 +600,8 @@ def run_train(args):
                                        f"NCCL gradient all-reduce + global-norm clip + AdamW, {b} clips/GPU in "
                                        f"micro-batches of {args.train_micro}, {FRAMES} frames, {H}x{W}, {J} joints, "
                                        f"random-init weights, backbone frozen (FREEZE_HRNET_WEIGHTS)",
-                           "native": "offset / mask convs and modulated DCN, forward and backward (C ABI kernels)",
-                           "library": "TransformerBlocks, RSB chains, pyramid 1x1 convs, prologue, loss: ATen ops "
+                           "native": "modulated DCN, offset / mask convs, every RSB conv and the pyramid 1x1 convs: forward and backward on C ABI kernels",
+                           "library": "TransformerBlocks, BatchNorm + ReLU of the RSB chains, prologue, loss: ATen ops "
                                       "under autograd (otpose_b200/model/train_ops.py)",
                            "clips_per_gpu": b, "heatmap": [H, W], "joints": J},
                 "clocks": clocks, "gpu_launches": int(launches),

@@ -4,11 +4,12 @@ STATUS -- read this before citing it.  The inference path of this package is han
 behind the C ABI.  The TRAINING path is a first version with a different split:
 
 * NATIVE forward + backward (C ABI kernels): the modulated deformable convolution
-  (``otp_mdcn_forward`` / ``otp_mdcn_backward``) and the dilated offset / mask convolutions that feed it
-  (``otp_conv2d`` / ``otp_conv2d_wgrad``) -- the stage that has no ATen equivalent.
-* LIBRARY ops under autograd (ATen: cuBLAS / cuDNN / elementwise): the TransformerBlocks, the RSB chains,
-  the pyramid 1x1 convs and the fusion prologue, composed below from the same arithmetic the reference's
-  modules execute (model/blocks.py:95-110, 264-279, 289-316, 400-452; model/RSB.py:81-139;
+  (``otp_mdcn_forward`` / ``otp_mdcn_backward``), the dilated offset / mask convolutions that feed it, every
+  convolution of the RSB chains and the two pyramid 1x1 convs (``otp_conv2d`` / ``otp_conv2d_wgrad`` behind
+  ``Conv2dFunction``).
+* LIBRARY ops under autograd (ATen: cuBLAS / cuDNN / elementwise): the TransformerBlocks (pointwise /
+  depthwise convs, Gram attention, LayerNorm, GELU, dropout), BatchNorm + ReLU of the RSB chains and the
+  fusion prologue, composed below from the same arithmetic the reference's modules execute (model/blocks.py:95-110, 264-279, 289-316, 400-452; model/RSB.py:81-139;
   model/OTPose.py:320-375).  They are explicit library calls, not a fallback of the CUDA path: eval-mode
   calls never reach this file and a training call never reaches the fused inference kernels.
 
@@ -91,8 +92,11 @@ def conv_transformer(enc, x):
 
 
 def conv_bn_relu(m, x):
-    """conv_bn_relu.forward (model/RSB.py:106-139); BatchNorm uses batch statistics when m.bn.training."""
-    x = F.conv2d(x, m.conv.weight, m.conv.bias, padding=m.kernel_size // 2)
+    """conv_bn_relu.forward (model/RSB.py:106-139); BatchNorm uses batch statistics when m.bn.training.
+    The convolution runs on the library's own kernels, forward and backward (Conv2dFunction: otp_conv2d /
+    otp_conv2d_wgrad); BatchNorm and ReLU are library ops."""
+    from .conv2d_fn import conv2d as conv2d_native
+    x = conv2d_native(x, m.conv.weight, m.conv.bias, 1)
     if m.has_bn:
         x = m.bn(x)
     return F.relu(x) if m.has_relu else x
@@ -163,7 +167,8 @@ def head_forward_train(model, rough_heatmaps, margin):
     c8 = x1.shape[1]
     y1 = torch.stack(conv_transformer(model.temporal_encoder1, x1), dim=1).contiguous().view(b, 3 * c8, h, w)
     y2 = torch.stack(conv_transformer(model.temporal_encoder2, x2), dim=1).contiguous().view(b, 3 * c8, h, w)
-    branches = torch.cat([model.final_layer1(y1), model.final_layer2(y2)], dim=1)
+    fl1, fl2 = model.final_layer1, model.final_layer2      # 1x1 convs 408 -> 17 on the library's own kernels
+    branches = torch.cat([conv2d_native(y1, fl1.weight, fl1.bias, 1), conv2d_native(y2, fl2.weight, fl2.bias, 1)], dim=1)
     def_heatmaps = chain_rsb(model.def_fuse, f["total_b"])
     trans = chain_rsb(model.offset_mask_combine_conv, torch.cat([branches, def_heatmaps], dim=1))
     ww = 1.0 / len(model.deformable_conv_dilations)
