@@ -305,11 +305,16 @@ tc_front1_kernel(BlockPack P, const float *__restrict__ x, const __grid_constant
         for (int g = 0; g < 6; ++g) {
           if (g * 8 < nq) {
             __half2 h2[4];
+            // LN1 affine of these 8 channels as four 16-byte broadcasts (not 16 scalar loads)
+            const float4 *w4 = reinterpret_cast<const float4 *>(V->ln1w + c_lo + g * 8);
+            const float4 *b4 = reinterpret_cast<const float4 *>(V->ln1b + c_lo + g * 8);
+            const float4 wa = w4[0], wb = w4[1], ba = b4[0], bb = b4[1];
+            const float lw[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+            const float lb[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int c = c_lo + g * 8 + 2 * e;
-              const float a0 = live ? fmaf((xr[g * 8 + 2 * e] - mu) * rstd, V->ln1w[c], V->ln1b[c]) : 0.f;
-              const float a1 = live ? fmaf((xr[g * 8 + 2 * e + 1] - mu) * rstd, V->ln1w[c + 1], V->ln1b[c + 1]) : 0.f;
+              const float a0 = live ? fmaf((xr[g * 8 + 2 * e] - mu) * rstd, lw[2 * e], lb[2 * e]) : 0.f;
+              const float a1 = live ? fmaf((xr[g * 8 + 2 * e + 1] - mu) * rstd, lw[2 * e + 1], lb[2 * e + 1]) : 0.f;
               if (S2) {   // centre tap stays in registers (fp32)
                 xr[g * 8 + 2 * e] = a0;
                 xr[g * 8 + 2 * e + 1] = a1;
