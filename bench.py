@@ -3,13 +3,16 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-A "step" is one pass of the whole hot path over one
-batch of synthetic person-clips: rough heat maps (5B,17,96,72) + margin -> fusion
+A "step" is one pass of the whole hot path over the step's
+synthetic person-clips: rough heat maps (5B,17,96,72) + margin -> fusion
 prologue -> 3 ConvTransformer encoders -> pyramid 1x1 convs -> RSB chains ->
 5 x (offset conv, mask conv, modulated DCN) -> refined heat maps -> get_final_preds.
+Default workload = BASELINE configs[2]: 512 clips per step, split evenly over the ranks
+(strong scaling), every rank running its shard as forward calls of 32 clips (the
+configs[1] batch); `--total-clips 0 --batch B` = B clips per GPU per step (weak scaling).
 One JSON line on stdout (rank 0).  N > 1 is launched by torchrun: one process per
-GPU, clips sharded by rank (weak scaling, no data-path collective; NCCL is only
-the barrier / max-over-ranks plumbing).
+GPU, no data-path collective (NCCL is only the barrier / max-over-ranks plumbing);
+`--train` (configs[3]) adds the gradient all-reduce.
 
 `--impl reference` times the reference's own CPU implementation of the path --
 the oracle port (reference ConvTransformer/RSB semantics in torch CPU fp32 +
@@ -44,10 +47,11 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=32,
                     help="person-clips per forward call (= per GPU per step unless --total-clips is given)")
-    ap.add_argument("--total-clips", type=int, default=0,
-                    help="BASELINE configs[2]: a FIXED total of clips per step split over the ranks (strong scaling, "
-                         "e.g. 512 -> 512/256/128/64 per GPU), each rank running its shard as forward calls of "
-                         "--batch clips")
+    ap.add_argument("--total-clips", type=int, default=512,
+                    help="BASELINE configs[2] (the default): a FIXED total of clips per step split over the ranks "
+                         "(strong scaling: 512 -> 512/256/128/64 per GPU at 1/2/4/8 GPUs), each rank running its shard "
+                         "as forward calls of --batch clips (32 = the configs[1] batch).  0 = weak scaling with "
+                         "--batch clips per GPU per step")
     ap.add_argument("--train", action="store_true",
                     help="BASELINE configs[3]: training step of the head (fwd + bwd + bucketed NCCL gradient "
                          "all-reduce + clip + AdamW), --batch clips per GPU (default 64 in this mode)")
@@ -221,8 +225,12 @@ def run_reference(args):
     cb = cpu_reference(args.cpu_clips, max(1, min(args.steps, 5)), min(args.warmup, 1))
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "clips/s", "n_gpus": args.gpus,
             "steps": max(1, min(args.steps, 5)), "warmup": min(args.warmup, 1), "ms_per_step": cb["ms_per_step"],
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(args.cpu_clips, "fp32"),
+            "higher_is_better": True, "scaling": "strong" if args.total_clips else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": dict(workload_config(args.total_clips // max(args.gpus, 1) if args.total_clips else args.batch,
+                                           "fp32", args.total_clips, args.gpus, min(args.batch, 32)),
+                           sample=f"each timed step is a bounded sample of that workload: {args.cpu_clips} clips on "
+                                  f"the host cores (per-clip work identical)"),
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}

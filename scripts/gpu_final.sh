@@ -7,7 +7,7 @@ timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${ta
 timeout 500 python bench.py --steps 20 --warmup 3 > gpurun_out/${tag}_bench_1gpu.json 2> gpurun_out/${tag}_bench_1gpu.err; echo "bench rc=$?"; tail -c 300 gpurun_out/${tag}_bench_1gpu.err
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_reference.json 2> gpurun_out/${tag}_bench_reference.err; echo "reference rc=$?"
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:^(?!.*pack)(?!.*fold_bias)(?!.*scale_cols).*$' -c 2400 --csv --log-file gpurun_out/${tag}_launches.csv \
-  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-cuda-graph --no-full-inference --roofline-seconds 0 > gpurun_out/${tag}_ncu_step.log 2>&1; echo "ncu list rc=$?"
+  python bench.py --total-clips 0 --steps 1 --warmup 3 --no-cpu-baseline --no-cuda-graph --no-full-inference --roofline-seconds 0 > gpurun_out/${tag}_ncu_step.log 2>&1; echo "ncu list rc=$?"
 python scripts/step_share.py gpurun_out/${tag}_launches.csv > gpurun_out/${tag}_step_share.txt 2>&1; head -30 gpurun_out/${tag}_step_share.txt
 timeout 400 ncu --set full --clock-control none --import-source on -k 'regex:tc_back|tc_front1|tc_apply|gram_project' --launch-skip 8 -c 4 -f -o gpurun_out/${tag}_prof_blocks \
   python scripts/prof_block.py 32 6912 1 4 > gpurun_out/${tag}_prof_blocks.log 2>&1; echo "ncu full rc=$?"

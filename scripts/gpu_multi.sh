@@ -10,6 +10,6 @@ try:
 except Exception as e: print('no line', e)
 PY
 }
-run weak --steps 20 --warmup 3
-run total512 --total-clips 512 --steps 5 --warmup 3
+run weak --total-clips 0 --steps 20 --warmup 3
+run total512 --steps 10 --warmup 3
 run train --train --steps 3 --warmup 1
