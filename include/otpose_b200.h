@@ -238,6 +238,14 @@ int otp_conv2d_wgrad(const float *x, long long x_bstride, const float *grad_out,
                      float *grad_weight, float *grad_bias, int b, int cin, int h, int w, int cout, int k,
                      int dilation, int accumulate, void *workspace, size_t workspace_bytes, otp_stream_t stream);
 
+/* a7 weight packing: eval-mode BatchNorm folded into the convolution in front of it
+ * (model/RSB.py:106-139: y = bn(conv(x))):  w_out[o] = w[o] * g_o,  b_out[o] = (b[o] - mean[o]) * g_o + beta[o],
+ * g_o = gamma[o] / sqrt(var[o] + eps).  `per_out` = cin * k * k weights per output channel.  With has_bn == 0
+ * the weights and the bias are copied (bias may be NULL: zeros). */
+int otp_conv_bn_fold(const float *weight, const float *bias, const float *gamma, const float *beta,
+                     const float *running_mean, const float *running_var, float eps, int has_bn, int cout,
+                     int per_out, float *weight_out, float *bias_out, otp_stream_t stream);
+
 /* a7, 16-bit tensor-core variant of otp_conv2d (dilation 1, w % 8 == 0, <= 96 channels):
  * implicit GEMM on tcgen05 over three pre-shifted 16-bit copies of the input rows (no im2col
  * tile), fp32 accumulate / bias / residual / output.  `packed` = otp_conv2d_tc_pack of the

@@ -389,56 +389,69 @@ block_back_kernel(BlockPack P, const float *__restrict__ x, const float *__restr
 }
 
 // ------------------------------------------------------------------ packing
-__global__ void pack_transpose_kernel(const float *__restrict__ src, int src_ld, int src_off,
-                                      float *__restrict__ dst, int N, int K, int NPAD) {
-  // dst[k][n] = src[n*src_ld + src_off + k], zero for n >= N
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= K * NPAD) return;
-  int k = e / NPAD, n = e % NPAD;
-  dst[e] = n < N ? src[(size_t)n * src_ld + src_off + k] : 0.f;
-}
-
-__global__ void pack_vec_kernel(const float *__restrict__ src, float *__restrict__ dst, int n, int npad,
-                                float fill_missing) {
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= npad) return;
-  dst[e] = e < n ? (src ? src[e] : fill_missing) : 0.f;
-}
-
-static void pack_T(const float *src, int src_ld, int src_off, float *dst, int N, int K, int NPAD,
-                   cudaStream_t st) {
-  pack_transpose_kernel<<<ceil_div(K * NPAD, 256), 256, 0, st>>>(src, src_ld, src_off, dst, N, K, NPAD);
-}
-static void pack_V(const float *src, float *dst, int n, int npad, float fill, cudaStream_t st) {
-  pack_vec_kernel<<<ceil_div(npad, 256), 256, 0, st>>>(src, dst, n, npad, fill);
+// Every section of the packed fp32 block is one JOB (a zero-padded vector copy or a transposed slice);
+// the whole job table travels as a kernel parameter and ONE launch packs the block (was 40 launches).
+struct PackJob {
+  const float *src;
+  float *dst;
+  int transpose;            // 0: dst[e] = e < N ? src[e] (or `fill` when src == NULL) : 0, e < NPAD
+                            // 1: dst[k][n] = n < N ? src[n * src_ld + src_off + k] : 0, k < K, n < NPAD
+  int src_ld, src_off, N, K, NPAD;
+  float fill;
+};
+constexpr int kMaxPackJobs = 48;
+struct PackJobs {
+  PackJob job[kMaxPackJobs];
+  int n;
+};
+__global__ void pack_jobs_kernel(const __grid_constant__ PackJobs J) {
+  const PackJob &j = J.job[blockIdx.y];
+  const int total = j.transpose ? j.K * j.NPAD : j.NPAD;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    if (j.transpose) {
+      const int k = e / j.NPAD, n = e % j.NPAD;
+      j.dst[e] = n < j.N ? j.src[(size_t)n * j.src_ld + j.src_off + k] : 0.f;
+    } else {
+      j.dst[e] = e < j.N ? (j.src ? j.src[e] : j.fill) : 0.f;
+    }
+  }
 }
 
 int block_pack_fp32(const otp_block_params *p, int c, float *f, cudaStream_t st) {
   const BlockPackLayout L = block_pack_layout(c);
   const int np = npad_of(c);
-  LaunchScope ls(K_PACK, st, 40);
-  pack_T(p->q_w, c, 0, f + L.wqT, c, c, np, st);
-  pack_T(p->k_w, c, 0, f + L.wkT, c, c, np, st);
-  pack_T(p->proj_w, c, 0, f + L.wpT, c, c, np, st);
-  pack_V(p->v_w, f + L.wv, c * c, c * c, 0.f, st);
+  PackJobs J{};
+  auto pack_T = [&](const float *src, int src_ld, int src_off, float *dst, int N, int K, int NPAD) {
+    J.job[J.n++] = PackJob{src, dst, 1, src_ld, src_off, N, K, NPAD, 0.f};
+  };
+  auto pack_V = [&](const float *src, float *dst, int n, int npad, float fill) {
+    J.job[J.n++] = PackJob{src, dst, 0, 0, 0, n, 0, npad, fill};
+  };
+  pack_T(p->q_w, c, 0, f + L.wqT, c, c, np);
+  pack_T(p->k_w, c, 0, f + L.wkT, c, c, np);
+  pack_T(p->proj_w, c, 0, f + L.wpT, c, c, np);
+  pack_V(p->v_w, f + L.wv, c * c, c * c, 0.f);
   for (int q = 0; q < 4; ++q) {
-    pack_T(p->mlp0_w + (size_t)q * c * c, c, 0, f + L.w1T + (size_t)q * c * np, c, c, np, st);
-    pack_T(p->mlp3_w, 4 * c, q * c, f + L.w2T + (size_t)q * c * np, c, c, np, st);
-    pack_V(p->mlp0_b + q * c, f + L.b1 + q * np, c, np, 0.f, st);
+    pack_T(p->mlp0_w + (size_t)q * c * c, c, 0, f + L.w1T + (size_t)q * c * np, c, c, np);
+    pack_T(p->mlp3_w, 4 * c, q * c, f + L.w2T + (size_t)q * c * np, c, c, np);
+    pack_V(p->mlp0_b + q * c, f + L.b1 + q * np, c, np, 0.f);
   }
-  pack_V(p->ln1_w, f + L.ln1_w, c, c, 1.f, st); pack_V(p->ln1_b, f + L.ln1_b, c, c, 0.f, st);
-  pack_V(p->ln2_w, f + L.ln2_w, c, c, 1.f, st); pack_V(p->ln2_b, f + L.ln2_b, c, c, 0.f, st);
-  pack_V(p->q_norm_w, f + L.qn_w, c, c, 1.f, st); pack_V(p->q_norm_b, f + L.qn_b, c, c, 0.f, st);
-  pack_V(p->k_norm_w, f + L.kn_w, c, c, 1.f, st); pack_V(p->k_norm_b, f + L.kn_b, c, c, 0.f, st);
-  pack_V(p->v_norm_w, f + L.vn_w, c, c, 1.f, st); pack_V(p->v_norm_b, f + L.vn_b, c, c, 0.f, st);
-  pack_V(p->q_conv_w, f + L.dwq, 3 * c, 3 * c, 0.f, st);
-  pack_V(p->k_conv_w, f + L.dwk, 3 * c, 3 * c, 0.f, st);
-  pack_V(p->v_conv_w, f + L.dwv, 3 * c, 3 * c, 0.f, st);
-  pack_V(p->q_b, f + L.bq, c, np, 0.f, st); pack_V(p->k_b, f + L.bk, c, np, 0.f, st);
-  pack_V(p->v_b, f + L.bv, c, np, 0.f, st); pack_V(p->proj_b, f + L.bp, c, np, 0.f, st);
-  pack_V(p->mlp3_b, f + L.b2, c, np, 0.f, st);
-  pack_V(p->scale_attn, f + L.sa, c, np, 1.f, st);
-  pack_V(p->scale_mlp, f + L.sm, c, np, 1.f, st);
+  pack_V(p->ln1_w, f + L.ln1_w, c, c, 1.f); pack_V(p->ln1_b, f + L.ln1_b, c, c, 0.f);
+  pack_V(p->ln2_w, f + L.ln2_w, c, c, 1.f); pack_V(p->ln2_b, f + L.ln2_b, c, c, 0.f);
+  pack_V(p->q_norm_w, f + L.qn_w, c, c, 1.f); pack_V(p->q_norm_b, f + L.qn_b, c, c, 0.f);
+  pack_V(p->k_norm_w, f + L.kn_w, c, c, 1.f); pack_V(p->k_norm_b, f + L.kn_b, c, c, 0.f);
+  pack_V(p->v_norm_w, f + L.vn_w, c, c, 1.f); pack_V(p->v_norm_b, f + L.vn_b, c, c, 0.f);
+  pack_V(p->q_conv_w, f + L.dwq, 3 * c, 3 * c, 0.f);
+  pack_V(p->k_conv_w, f + L.dwk, 3 * c, 3 * c, 0.f);
+  pack_V(p->v_conv_w, f + L.dwv, 3 * c, 3 * c, 0.f);
+  pack_V(p->q_b, f + L.bq, c, np, 0.f); pack_V(p->k_b, f + L.bk, c, np, 0.f);
+  pack_V(p->v_b, f + L.bv, c, np, 0.f); pack_V(p->proj_b, f + L.bp, c, np, 0.f);
+  pack_V(p->mlp3_b, f + L.b2, c, np, 0.f);
+  pack_V(p->scale_attn, f + L.sa, c, np, 1.f);
+  pack_V(p->scale_mlp, f + L.sm, c, np, 1.f);
+  if (J.n > kMaxPackJobs) return fail_arg("pack job table overflow");
+  LaunchScope ls(K_PACK, st, 1);
+  pack_jobs_kernel<<<dim3(ceil_div(c * np, 256), J.n), 256, 0, st>>>(J);
   return check_launch("block_pack");
 }
 

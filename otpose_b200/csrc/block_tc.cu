@@ -355,29 +355,42 @@ __device__ __forceinline__ unsigned short to_fmt(float v) {
   if constexpr (FMT == 0) return to16<false>(v);
   return to16<false>(v - __bfloat162float(__float2bfloat16_rn(v)));
 }
-// operand image of src[row0 + r][col0 + k] * colscale[col0 + k]   (zero padded)
-template <int FMT>
-__global__ void pack_image_kernel(const float *__restrict__ src, int ld, int row0, int col0, int rows_valid,
-                                  int cols_valid, const float *__restrict__ colscale, uint8_t *__restrict__ dst,
-                                  int rows_pad, int cols_pad) {
+// ALL weight pieces of a block in one launch: blockIdx.y = piece (Wp 0..2, W1 chunk c slice s 3 + 3c + s, W2 chunk
+// c slice s 15 + 3c + s), blockIdx.z = set (0 bf16 hi, 1 fp16, 2 bf16 lo: W1 / W2 only).  A piece is the
+// [144 rows][48 K] operand image of a K-slice; LayerNorm-2's scale is folded into W1's columns, and column 136
+// (= column 40 of K-slice 2) of the Wp / W1 pieces carries the bias that rides in the MMA against the
+// activation tile's ones column (b1f = b_1 + W_1 beta_2, computed by fold_bias_kernel before this launch).
+struct PiecePackArgs {
+  const float *proj_w, *proj_b, *mlp0_w, *mlp3_w, *ln2_w, *b1f;
+  uint8_t *base;
+  size_t img_bytes, lo;
+};
+__global__ void pack_pieces_kernel(const PiecePackArgs A) {
+  const int idx = blockIdx.y, f = blockIdx.z;
+  if (f == 2 && idx < kPiecesPerImage) return;   // no lo term for Wp
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= rows_pad * cols_pad) return;
-  const int r = e / cols_pad, k = e % cols_pad;
+  if (e >= kKP * kPieceK) return;
+  const int r = e / kPieceK, k = e % kPieceK;
+  const int fam = idx < kPiecesPerImage ? 0 : (idx < kPiecesPerImage * (1 + kNChunk) ? 1 : 2);
+  const int c = fam == 0 ? 0 : (idx - kPiecesPerImage * (fam == 1 ? 1 : 1 + kNChunk)) / kPiecesPerImage;
+  const int sl = idx % kPiecesPerImage;
   float v = 0.f;
-  if (r < rows_valid && k < cols_valid) {
-    v = src[(size_t)(row0 + r) * ld + col0 + k];
-    if (colscale) v *= colscale[col0 + k];
+  if (fam == 0) {          // Wp: rows = output channels, K = input channels
+    const int col = sl * kPieceK + k;
+    if (r < kC && col < kC) v = A.proj_w[(size_t)r * kC + col];
+    else if (r < kC && col == kC) v = A.proj_b[r];
+  } else if (fam == 1) {   // W1 chunk c: rows = hidden c*144 + r, K = input channels, LN2 scale folded in
+    const int hrow = c * kNH + r, col = sl * kPieceK + k;
+    if (hrow < 4 * kC && col < kC) v = A.mlp0_w[(size_t)hrow * kC + col] * A.ln2_w[col];
+    else if (hrow < kHidPad && col == kC) v = A.b1f[hrow];
+  } else {                 // W2 chunk c: rows = output channels, K = hidden c*144 + 48 s + k
+    const int hcol = c * kNH + sl * kPieceK + k;
+    if (r < kC && hcol < 4 * kC) v = A.mlp3_w[(size_t)r * 4 * kC + hcol];
   }
-  *reinterpret_cast<unsigned short *>(dst + cm_offset(r, k, (cols_pad / 8) * 128, 128)) = to_fmt<FMT>(v);
-}
-// column `col` of an operand image <- bias[row0 + r] (r < rows_valid): the bias rides in the MMA
-// against a ones column of the activation tile
-template <int FMT>
-__global__ void pack_bias_col_kernel(const float *__restrict__ bias, int row0, int rows_valid, uint8_t *__restrict__ dst,
-                                     int cols_pad, int col) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < rows_valid)
-    *reinterpret_cast<unsigned short *>(dst + cm_offset(r, col, (cols_pad / 8) * 128, 128)) = to_fmt<FMT>(bias[row0 + r]);
+  uint8_t *dst = f < 2 ? A.base + f * A.img_bytes + (size_t)idx * kPiece
+                       : A.base + A.lo + (size_t)(idx - kPiecesPerImage) * kPiece;
+  const unsigned short h = f == 1 ? to_fmt<1>(v) : (f == 0 ? to_fmt<0>(v) : to_fmt<2>(v));
+  *reinterpret_cast<unsigned short *>(dst + cm_offset(r, k, kRS48, 128)) = h;
 }
 // out[n] = bias[n] + sum_c w[n][c] * lnb[c]  (n < rows), 0 for the padding
 __global__ void fold_bias_kernel(const float *__restrict__ w, const float *__restrict__ bias,
@@ -396,26 +409,6 @@ __global__ void scale_cols_kernel(const float *__restrict__ w, const float *__re
                                   int rows, int cols) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e < rows * cols) out[e] = w[e] * g[e % cols];
-}
-
-void pack_image(int fmt, const float *src, int ld, int row0, int col0, int rv, int cv, const float *colscale,
-                uint8_t *dst, int rp, int cp, cudaStream_t st) {
-  const int g = ceil_div(rp * cp, 256);
-  if (fmt == 1)
-    pack_image_kernel<1><<<g, 256, 0, st>>>(src, ld, row0, col0, rv, cv, colscale, dst, rp, cp);
-  else if (fmt == 0)
-    pack_image_kernel<0><<<g, 256, 0, st>>>(src, ld, row0, col0, rv, cv, colscale, dst, rp, cp);
-  else
-    pack_image_kernel<2><<<g, 256, 0, st>>>(src, ld, row0, col0, rv, cv, colscale, dst, rp, cp);
-}
-void pack_bias_col(int fmt, const float *bias, int row0, int rv, uint8_t *dst, int cp, int col, cudaStream_t st) {
-  const int g = ceil_div(rv, 256);
-  if (fmt == 1)
-    pack_bias_col_kernel<1><<<g, 256, 0, st>>>(bias, row0, rv, dst, cp, col);
-  else if (fmt == 0)
-    pack_bias_col_kernel<0><<<g, 256, 0, st>>>(bias, row0, rv, dst, cp, col);
-  else
-    pack_bias_col_kernel<2><<<g, 256, 0, st>>>(bias, row0, rv, dst, cp, col);
 }
 
 constexpr size_t kApplySmem = (size_t)kTile144 + kW144 + kApplyStage;
@@ -520,28 +513,7 @@ int block_tc_pack(const otp_block_params *p, int c, void *packed_tc, cudaStream_
   if (c != kC) return OTP_OK;
   constexpr TcPack L = tc_pack_layout();
   uint8_t *base = static_cast<uint8_t *>(packed_tc);
-  LaunchScope ls(K_PACK, st, 100);
-  // piece (image base, K-slice s) of set f: 0 bf16 (hi), 1 fp16, 2 bf16 lo terms (W1 / W2 only)
-  auto piece = [&](int f, size_t img_off, int s) {
-    uint8_t *set = f < 2 ? base + f * L.img_bytes : base + L.lo - L.w1;
-    return set + img_off + (size_t)s * kPiece;
-  };
-  for (int f = 0; f < 3; ++f) {
-    for (int s = 0; s < kPiecesPerImage; ++s) {
-      const int cv = min(kPieceK, kC - s * kPieceK);   // valid input channels of this K-slice (48, 48, 40)
-      if (f < 2) pack_image(f, p->proj_w, kC, 0, s * kPieceK, kC, cv, nullptr, piece(f, L.wp, s), kKP, kPieceK, st);
-      for (int c = 0; c < kNChunk; ++c) {
-        // W1 chunk c: hidden rows c*144.., K = input channels (LN2 affine folded: W1' = W1 diag(g2))
-        const int hv = max(0, min(kNH, 4 * kC - c * kNH));
-        pack_image(f, p->mlp0_w, kC, c * kNH, s * kPieceK, hv, cv, p->ln2_w,
-                   piece(f, L.w1 + (size_t)c * kPiecesPerImage * kPiece, s), kNH, kPieceK, st);
-        // W2 chunk c: all output rows, K = hidden c*144 + 48 s ..
-        const int kv = max(0, min(kPieceK, 4 * kC - c * kNH - s * kPieceK));
-        pack_image(f, p->mlp3_w, 4 * kC, 0, c * kNH + s * kPieceK, kC, kv, nullptr,
-                   piece(f, L.w2 + (size_t)c * kPiecesPerImage * kPiece, s), kKP, kPieceK, st);
-      }
-    }
-  }
+  LaunchScope ls(K_PACK, st, 8);
   scale_cols_kernel<<<ceil_div(kC * kC, 256), 256, 0, st>>>(p->v_w, p->v_norm_w, reinterpret_cast<float *>(base + L.wvp),
                                                             kC, kC);
   fold_bias_kernel<<<1, 256, 0, st>>>(p->v_w, p->v_b, p->v_norm_b, reinterpret_cast<float *>(base + L.bvp), kC, kC, kKP);
@@ -554,16 +526,10 @@ int block_tc_pack(const otp_block_params *p, int c, void *packed_tc, cudaStream_
                                                               1.0f / sqrtf((float)kHS), reinterpret_cast<float *>(base + L.wqaT));
   pack_aug_T_kernel<<<ceil_div(kKP * kKP, 256), 256, 0, st>>>(p->k_w, p->k_norm_w, reinterpret_cast<const float *>(base + L.bkp),
                                                               1.0f, reinterpret_cast<float *>(base + L.wkaT));
-  // biases folded into operand column 136 (= column 40 of K-slice 2): b_p into Wp, b_1 + W_1 beta_2 into the
-  // W1 chunks (the lo pieces carry the bias's bf16 remainder in bfloat16 mode)
-  const float *b1f = reinterpret_cast<const float *>(base + L.b1p);
-  constexpr int kBiasSlice = kC / kPieceK, kBiasCol = kC % kPieceK;
-  for (int f = 0; f < 3; ++f) {
-    if (f < 2) pack_bias_col(f, p->proj_b, 0, kC, piece(f, L.wp, kBiasSlice), kPieceK, kBiasCol, st);
-    for (int c = 0; c < kNChunk; ++c)
-      pack_bias_col(f, b1f, c * kNH, kNH, piece(f, L.w1 + (size_t)c * kPiecesPerImage * kPiece, kBiasSlice), kPieceK,
-                    kBiasCol, st);
-  }
+  // all 27 weight pieces x {bf16 hi, fp16, bf16 lo} in one launch (b1f is ready: same stream)
+  const PiecePackArgs A{p->proj_w, p->proj_b, p->mlp0_w, p->mlp3_w, p->ln2_w, reinterpret_cast<const float *>(base + L.b1p),
+                        base, L.img_bytes, L.lo};
+  pack_pieces_kernel<<<dim3(ceil_div(kKP * kPieceK, 256), kNumPieces, 3), 256, 0, st>>>(A);
   return check_launch("block_tc_pack");
 }
 

@@ -284,6 +284,35 @@ static bool launch_strip(const float *x, long long x_bs, const float *xa, long l
 
 using namespace otp;
 
+__global__ void conv_bn_fold_kernel(const float *__restrict__ w, const float *__restrict__ b, const float *__restrict__ gamma,
+                                    const float *__restrict__ beta, const float *__restrict__ mean,
+                                    const float *__restrict__ var, float eps, int has_bn, int cout, int per_out,
+                                    float *__restrict__ w_out, float *__restrict__ b_out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= cout * per_out + cout) return;
+  const int o = e < cout * per_out ? e / per_out : e - cout * per_out;
+  const float g = has_bn ? gamma[o] / sqrtf(var[o] + eps) : 1.f;
+  if (e < cout * per_out) {
+    w_out[e] = w[e] * g;
+  } else {
+    const float bb = b ? b[o] : 0.f;
+    b_out[o] = has_bn ? (bb - mean[o]) * g + beta[o] : bb;
+  }
+}
+
+extern "C" int otp_conv_bn_fold(const float *weight, const float *bias, const float *gamma, const float *beta,
+                                const float *running_mean, const float *running_var, float eps, int has_bn, int cout,
+                                int per_out, float *weight_out, float *bias_out, otp_stream_t stream) {
+  OTP_REQUIRE(cout > 0 && per_out > 0 && weight && weight_out && bias_out);
+  OTP_REQUIRE(!has_bn || (gamma && beta && running_mean && running_var));
+  cudaStream_t st = (cudaStream_t)stream;
+  LaunchScope ls(K_PACK, st);
+  const int n = cout * per_out + cout;
+  conv_bn_fold_kernel<<<ceil_div(n, 256), 256, 0, st>>>(weight, bias, gamma, beta, running_mean, running_var, eps, has_bn,
+                                                        cout, per_out, weight_out, bias_out);
+  return check_launch("conv_bn_fold_kernel");
+}
+
 extern "C" int otp_conv2d(const float *x, long long x_bstride, const float *x_add,
                           long long x_add_bstride, const float *weight, const float *bias,
                           const float *residual, long long residual_bstride, float *y,

@@ -36,13 +36,20 @@ class conv_bn_relu(nn.Module):
               self.bn.running_var]
         key = tuple((id(p), p.data_ptr(), p._version) for p in ps)   # the entry below keeps `ps` alive
         if self._folded is None or key != self._folded_key:
-            with torch.no_grad():
-                w, b = self.conv.weight.detach().float(), self.conv.bias.detach().float()
-                if self.has_bn:
-                    g = self.bn.weight.detach() / torch.sqrt(self.bn.running_var + self.bn.eps)
-                    w = w * g.view(-1, 1, 1, 1)
-                    b = (b - self.bn.running_mean) * g + self.bn.bias.detach()
-                self._folded = (w.contiguous(), b.contiguous())
+            lib = _lib.load()
+            wsrc, dev = self.conv.weight.detach(), self.conv.weight.device
+            _lib.require_cuda(wsrc)
+            w = torch.empty_like(wsrc, dtype=torch.float32, memory_format=torch.contiguous_format)
+            b = torch.empty(wsrc.shape[0], dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):      # one library launch (packing stays inside the library)
+                _lib.check(lib.otp_conv_bn_fold(
+                    _lib.dptr(wsrc), _lib.dptr(self.conv.bias.detach() if self.conv.bias is not None else None,
+                                               allow_none=True),
+                    _lib.dptr(self.bn.weight.detach()), _lib.dptr(self.bn.bias.detach()),
+                    _lib.dptr(self.bn.running_mean), _lib.dptr(self.bn.running_var), float(self.bn.eps),
+                    int(self.has_bn), wsrc.shape[0], wsrc[0].numel(), w.data_ptr(), b.data_ptr(),
+                    _lib.stream_ptr(dev)), "otp_conv_bn_fold")
+            self._folded = (w, b)
             self._folded_key = key
             self._folded_src = ps
         return self._folded

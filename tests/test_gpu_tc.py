@@ -108,10 +108,15 @@ def test_tensor_core_conv_vs_float64(cin, cout, k, b, h, w, add, res, prec, tol)
     x = torch.randn(b, cin, h, w)
     xa = torch.randn_like(x) if add else None
     r = torch.randn(b, cout, h, w) if res else None
-    wt, bias = m.folded()
-    ref = F.conv2d((x + (xa if add else 0)).double(), wt.double(), bias.double(), padding=k // 2)
-    ref = F.relu(ref + (r.double() if res else 0))
     m = m.cuda()
+    wt, bias = (t.cpu() for t in m.folded())          # otp_conv_bn_fold (library launch: CUDA tensors only)
+    with torch.no_grad():                             # ... checked against the module's own parameters
+        g = m.bn.weight.cpu().double() / torch.sqrt(m.bn.running_var.cpu().double() + m.bn.eps)
+        w64 = m.conv.weight.cpu().double() * g.view(-1, 1, 1, 1)
+        b64 = (m.conv.bias.cpu().double() - m.bn.running_mean.cpu().double()) * g + m.bn.bias.cpu().double()
+    assert float((wt.double() - w64).abs().max()) < 1e-6 and float((bias.double() - b64).abs().max()) < 1e-6
+    ref = F.conv2d((x + (xa if add else 0)).double(), w64, b64, padding=k // 2)
+    ref = F.relu(ref + (r.double() if res else 0))
     assert _lib.load().otp_conv2d_tc_supported(cin, cout, h, w, k) == 1
     xg, xag, rg = x.cuda(), xa.cuda() if add else None, r.cuda() if res else None
     for p, t in (("fp32", 1e-5), (prec, tol)):
