@@ -183,6 +183,19 @@ int otp_block_forward(const void *packed, const float *x, float *y, int b, int c
                       int stride, int precision, void *workspace, size_t workspace_bytes,
                       otp_stream_t stream);
 
+/* a2-a5, the whole C = 17 / one-head flow encoder (model/OTPose.py:214-216, 331-335;
+ * model/ConvVideoTransformer.py:147-170) in the 16-bit modes: y (B,17,T) = stem blocks (x + pe[:, :t]), all
+ * `nblocks` stride-1 TransformerBlocks in ONE launch -- a thread-block cluster per clip keeps the residual
+ * stream in shared memory, the channel Gram is reduced through distributed shared memory in a fixed order
+ * (IEEE half mma.sync operands, fp32 accumulate / LayerNorms / softmax).  packed_blocks[i] = otp_block_pack of
+ * block i (HOST array of device pointers); pe may be NULL.  `supported` = 1 when (c, n_head, t, nblocks) is
+ * built (c = 17, n_head = 1, t <= 13824, nblocks <= 8); otherwise call otp_block_forward per block. */
+int otp_flow_encoder_supported(int c, int n_head, int t, int nblocks);
+size_t otp_flow_encoder_workspace_bytes(int b, int t);
+int otp_flow_encoder_forward(const void *const *packed_blocks, int nblocks, const float *x, const float *pe,
+                             int pe_stride, float *y, int b, int t, void *workspace, size_t workspace_bytes,
+                             otp_stream_t stream);
+
 /* y = x + pe[:, :t]   (x,y (B,C,T); pe (C, >=T), row stride pe_stride) */
 int otp_add_pos_embd(const float *x, const float *pe, int pe_stride, float *y, int b, int c, int t,
                      otp_stream_t stream);

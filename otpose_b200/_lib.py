@@ -52,6 +52,9 @@ SIGNATURES = {
     "otp_block_pack": (i32, [C.POINTER(BlockParams), i32, i32, vp, sz, vp]),
     "otp_block_workspace_bytes": (sz, [i32, i32, i32, i32, i32, i32]),
     "otp_block_forward": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, sz, vp]),
+    "otp_flow_encoder_supported": (i32, [i32, i32, i32, i32]),
+    "otp_flow_encoder_workspace_bytes": (sz, [i32, i32]),
+    "otp_flow_encoder_forward": (i32, [vp, i32, vp, vp, i32, vp, i32, i32, vp, sz, vp]),
     "otp_add_pos_embd": (i32, [vp, vp, i32, vp, i32, i32, i32, vp]),
     "otp_upsample_linear": (i32, [vp, vp, i32, i32, i32, i32, vp]),
     "otp_pyramid_conv1x1": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, vp, i64, vp]),

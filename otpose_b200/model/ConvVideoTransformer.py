@@ -34,6 +34,7 @@ class ConvTransformer(nn.Module):
         self.mha_win_size = [mha_win_size] * len(self.fpn_strides) if isinstance(mha_win_size, int) \
             else mha_win_size
         self.precision = precision
+        self.fused_stem = True      # 16-bit modes, C = 17: one cluster launch for the whole stem (block_flow.cu)
         if use_abs_pe:
             self.register_buffer("pos_embd", get_sinusoid_encoding(max_len, n_embd) / (n_embd ** 0.5))
         self.embd = nn.ModuleList()
@@ -88,6 +89,22 @@ class ConvTransformer(nn.Module):
         if not x.is_contiguous():
             x = x.contiguous()
         st = _lib.stream_ptr(x.device)
+        if (self.precision != "fp32" and b > 0 and not self.branch and len(self.stem) > 0 and self.fused_stem
+                and lib.otp_flow_encoder_supported(c, self.n_head, t, len(self.stem))):
+            # the narrow flow encoder in the 16-bit modes: positional embedding + every stem block in ONE
+            # cluster launch (csrc/block_flow.cu); operands are IEEE half in both 16-bit modes
+            import ctypes as C
+            pe, stride = self.pos_embd_for(t) if self.use_abs_pe else (None, 0)
+            packs = [blk.packed_weights() for blk in self.stem]
+            ptrs = (C.c_void_p * len(packs))(*[p_.data_ptr() for p_ in packs])
+            nws = lib.otp_flow_encoder_workspace_bytes(b, t)
+            ws = _lib.workspace.get(nws, x.device, "flow")
+            y = torch.empty_like(x)
+            with torch.cuda.device(x.device):
+                _lib.check(lib.otp_flow_encoder_forward(ptrs, len(packs), _lib.dptr(x), _lib.dptr(pe, allow_none=True),
+                                                        stride, y.data_ptr(), b, t, ws.data_ptr(), ws.numel(), st),
+                           "otp_flow_encoder_forward")
+            return (y,)
         with torch.cuda.device(x.device):
             if self.use_abs_pe and b > 0:
                 pe, stride = self.pos_embd_for(t)

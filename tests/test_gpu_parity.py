@@ -420,6 +420,35 @@ def test_tensor_core_block_vs_cuda_core_block(b, t, stride, fmt, tol):
     assert torch.equal(got, blk(x, precision=fmt))     # deterministic
 
 
+@pytest.mark.parametrize("b,h,w", [(2, 24, 20), (3, 16, 12), (1, 96, 72), (32, 96, 72), (2, 128, 96), (5, 7, 5)])
+def test_fused_flow_encoder_vs_per_block_fp32(b, h, w):
+    """C = 17 flow encoder in the 16-bit modes: ONE cluster launch for the positional embedding and the six
+    stem blocks (csrc/block_flow.cu; cluster sizes 1 / 2 / 4 / 8, ragged last run, halo tokens) against the
+    fp32 per-block kernels of the same module, and against the oracle at the small sizes."""
+    t = h * w
+    m = ConvTransformer(17, 17, n_head=1, n_embd_ks=3, max_len=t, arch=(0, 6, 0), proj_pdrop=0.1, path_pdrop=0.1,
+                        h=h, precision="fp16")
+    sd = syn.fill_state_dict({k: v.shape for k, v in m.state_dict().items()}, seed=11)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    assert _lib.load().otp_flow_encoder_supported(17, 1, t, 6) == 1
+    x = cuda(np.random.default_rng(b * 1000 + t).standard_normal((b, 17, h, w)).astype(np.float32))
+    got = m(x)[0]
+    m.precision = "fp32"
+    ref = m(x)[0]
+    m.precision = "fp16"
+    assert got.shape == ref.shape and torch.isfinite(got).all()
+    assert rel(got, ref) < TOL["fp16"], rel(got, ref)
+    assert torch.equal(got, m(x)[0])                         # fixed-order Gram reduction through DSMEM
+    one = m(x[b - 1:].contiguous())[0]                       # clips are independent; cluster size may differ
+    assert rel(one, got[b - 1:]) < 2e-3                      # (another reduction order: half-rounding level)
+    if t <= 480:
+        o = ho.conv_transformer(sd, "", x.cpu(), 1, (0, 6, 0))[0]
+        assert rel(got, o) < TOL["fp16"]
+    m.fused_stem = False                                      # the per-block path stays reachable
+    assert rel(m(x)[0], ref) < 1e-6
+
+
 def test_fp16_operands_saturate_instead_of_overflowing():
     """IEEE-half operands have a finite range (65504).  With trained checkpoints GELU(hidden), att @ v and
     the post-ReLU RSB maps are unbounded, so every fp32 -> half operand conversion saturates
