@@ -259,6 +259,21 @@ int otp_conv_bn_fold(const float *weight, const float *bias, const float *gamma,
                      const float *running_mean, const float *running_var, float eps, int has_bn, int cout,
                      int per_out, float *weight_out, float *bias_out, otp_stream_t stream);
 
+/* a7, 16-bit modes: a whole RSB_BLOCK (model/RSB.py:26-103: conv_bn_relu1, the ten dense-connected 3x3
+ * conv_bn_relu2_* convs, conv_bn_relu3 + skip / downsample + ReLU) in one launch -- two for the widest block -- with
+ * every intermediate map in shared-memory row rings (csrc/rsb_fused.cu).  `weights` / `biases`: HOST arrays of 13
+ * device pointers to the BN-FOLDED fp32 convs (otp_conv_bn_fold) in the order conv_bn_relu1, conv_bn_relu2_{1_1,
+ * 2_1, 2_2, 3_1, 3_2, 3_3, 4_1, 4_2, 4_3, 4_4}, conv_bn_relu3, downsample (entry 12 ignored without downsample).
+ * x (B,cin,H,W) / y (B,planes,H,W) fp32 with batch strides in elements (channel slices of wider buffers). */
+int otp_rsb_block_supported(int cin, int planes, int h, int w);
+size_t otp_rsb_block_pack_bytes(int cin, int planes, int has_downsample);
+int otp_rsb_block_pack(const float *const *weights, const float *const *biases, int cin, int planes,
+                       int has_downsample, void *packed, size_t packed_bytes, otp_stream_t stream);
+size_t otp_rsb_block_workspace_bytes(int b, int cin, int planes, int h, int w);
+int otp_rsb_block_forward(const void *packed, const float *x, long long x_bstride, float *y, long long y_bstride,
+                          int b, int cin, int planes, int has_downsample, int h, int w, void *workspace,
+                          size_t workspace_bytes, otp_stream_t stream);
+
 /* a7, 16-bit tensor-core variant of otp_conv2d (dilation 1, w % 8 == 0, <= 96 channels):
  * implicit GEMM on tcgen05 over three pre-shifted 16-bit copies of the input rows (no im2col
  * tile), fp32 accumulate / bias / residual / output.  `packed` = otp_conv2d_tc_pack of the

@@ -106,6 +106,43 @@ class RSB_BLOCK(nn.Module):
         self.relu = nn.ReLU(inplace=True)
         self.downsample = downsample
         self.planes = planes
+        self.fused = True           # 16-bit modes: the whole block in one / two launches (csrc/rsb_fused.cu)
+        self._fused_packed = None
+        self._fused_key = None
+
+    _ORDER = ("conv_bn_relu1", "conv_bn_relu2_1_1", "conv_bn_relu2_2_1", "conv_bn_relu2_2_2", "conv_bn_relu2_3_1",
+              "conv_bn_relu2_3_2", "conv_bn_relu2_3_3", "conv_bn_relu2_4_1", "conv_bn_relu2_4_2", "conv_bn_relu2_4_3",
+              "conv_bn_relu2_4_4", "conv_bn_relu3")
+
+    def _forward_fused(self, x):
+        """RSB.py:81-103 in the 16-bit modes: ``otp_rsb_block_forward`` on the BN-folded convs (IEEE half operands,
+        fp32 accumulate; every intermediate map stays in shared memory)."""
+        import ctypes as C
+        lib = _lib.load()
+        b, cin, h, w = x.shape
+        dev = x.device
+        convs = [getattr(self, n) for n in self._ORDER] + ([self.downsample] if self.downsample is not None else [])
+        folded = [m.folded() for m in convs]
+        key = tuple(m._folded_key for m in convs)
+        has_ds = int(self.downsample is not None)
+        with torch.cuda.device(dev):
+            if self._fused_packed is None or key != self._fused_key:
+                nbytes = lib.otp_rsb_block_pack_bytes(cin, self.planes, has_ds)
+                buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                wp = (C.c_void_p * 13)(*([f[0].data_ptr() for f in folded] + [None] * (13 - len(folded))))
+                bp = (C.c_void_p * 13)(*([f[1].data_ptr() for f in folded] + [None] * (13 - len(folded))))
+                _lib.check(lib.otp_rsb_block_pack(wp, bp, cin, self.planes, has_ds, buf.data_ptr(), nbytes,
+                                                  _lib.stream_ptr(dev)), "otp_rsb_block_pack")
+                self._fused_packed, self._fused_key = buf, key
+            xc = x if x.is_contiguous() else x.contiguous()
+            out = torch.empty((b, self.planes, h, w), dtype=torch.float32, device=dev)
+            nws = lib.otp_rsb_block_workspace_bytes(b, cin, self.planes, h, w)
+            ws = _lib.workspace.get(nws, dev, "rsb")
+            _lib.check(lib.otp_rsb_block_forward(self._fused_packed.data_ptr(), _lib.dptr(xc), cin * h * w,
+                                                 out.data_ptr(), self.planes * h * w, b, cin, self.planes, has_ds, h, w,
+                                                 ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev)),
+                       "otp_rsb_block_forward")
+        return out
 
     def forward(self, x):
         """RSB.py:81-103.  Intermediate layout: `spx` (B,4bc,H,W) and one (B,10bc,H,W)
@@ -117,6 +154,9 @@ class RSB_BLOCK(nn.Module):
             return train_ops.rsb_block(self, x)
         _lib.require_cuda(x)
         b, cin, h, w = x.shape
+        if self.fused and self.conv_bn_relu1.precision != "fp32" and b > 0 and x.dtype == torch.float32 \
+                and _lib.load().otp_rsb_block_supported(cin, self.planes, h, w):
+            return self._forward_fused(x)
         p = h * w
         bc = self.branch_ch
         dev = x.device

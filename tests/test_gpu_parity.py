@@ -518,6 +518,33 @@ def test_rsb_w8_vs_reference_golden(precision, tol):
     assert rel(m(cuda(g["x"])), g["out"]) < tol
 
 
+@pytest.mark.parametrize("cin,cout", [(17, 17), (51, 32)])
+@pytest.mark.parametrize("b,h,w", [(2, 96, 72), (3, 50, 37), (1, 24, 20), (1, 128, 96), (33, 16, 16), (2, 9, 7)])
+def test_fused_rsb_block_vs_per_conv_fp32(cin, cout, b, h, w):
+    """a7, 16-bit modes: each RSB_BLOCK as one launch (two for the 51 -> 32 / 32 -> 32 blocks) of the streaming
+    row-ring kernel (csrc/rsb_fused.cu; row / column bands with halos, rows above and below the image, ragged
+    last pixel tile, any width) against the fp32 per-conv path of the same modules and the oracle."""
+    m = CHAIN_RSB_BLOCKS(cin, cout, 2)
+    sd = syn.fill_state_dict({k: v.shape for k, v in m.state_dict().items()}, seed=5)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    assert _lib.load().otp_rsb_block_supported(cin, cout, h, w) == 1
+    x = cuda(np.random.default_rng(b * 100 + h).standard_normal((b, cin, h, w)).astype(np.float32))
+    ref = m(x)
+    for mod in m.modules():
+        if hasattr(mod, "precision"):
+            mod.precision = "fp16"
+    got = m(x)
+    assert got.shape == ref.shape and torch.isfinite(got).all()
+    assert rel(got, ref) < 5e-3, rel(got, ref)
+    assert torch.equal(got, m(x))
+    if h * w <= 2000:
+        assert rel(got, ho.chain_rsb({k: v.cpu() for k, v in m.state_dict().items()}, "", x.cpu(), 2)) < 5e-3
+    for blk in m.layers:          # the per-conv tcgen05 path stays reachable
+        blk.fused = False
+    assert rel(m(x), ref) < 5e-3
+
+
 # ----------------------------------------------------------------- whole head
 def build_head(h, w, precision, seed=2024):
     model = OTPose(default_cfg((h, w)), precision=precision)
