@@ -123,6 +123,9 @@ def algorithmic_work(b, t=T, precision="fp32"):
     rsb = (0.116e9 + 0.868e9) * t / T * b
     offmask = 5 * (1.218e9 + 0.609e9) * t / T * b
     w["conv2d"] = ("tensor", rsb + offmask if precision == "fp32" else rsb)
+    # 16-bit modes: the RSB chains run the per-level mma.sync kernels, the C = 17 flow encoder its one cluster launch
+    w["rsb_block"] = ("tensor", rsb)
+    w["flow_encoder"] = ("tensor", flops(lambda c, tt: 26 * c * c * tt, [(c, tt) for c, tt in blocks if c != C8]))
     w["tc_offset_mask_dcn"] = ("tensor", offmask + 5 * 0.036e9 * t / T * b)
     # HBM-bound: read offsets+masks (459 ch) + x (17) + write/accumulate out (17), fp32, x5 dilations
     w["mdcn_fwd"] = ("hbm", 5.0 * (459 + 17 + 17) * t * 4 * b)

@@ -203,7 +203,8 @@ __global__ void __launch_bounds__(FTH, 1) flow_encoder_kernel(const __grid_const
     float v[6];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      const float2 t = *reinterpret_cast<const float2 *>(xr + 8 * j);
+      // slots 4, 5 of the lanes q != 0 are padding: no load (it would reach into the next token's row)
+      const float2 t = (j < 2 || q0) ? *reinterpret_cast<const float2 *>(xr + 8 * j) : make_float2(0.f, 0.f);
       v[2 * j] = t.x, v[2 * j + 1] = t.y;
     }
     ln_quad(v, q0);
@@ -480,7 +481,9 @@ __global__ void __launch_bounds__(FTH, 1) flow_encoder_kernel(const __grid_const
             mma3(p, oh.k0, ol.k0, wp_f[(0 * 3 + nt) * 32 + lane], wp_l[(0 * 3 + nt) * 32 + lane]);
             mma3_k1(p, oh.k1, ol.k1, wp_f[(1 * 3 + nt) * 32 + lane], wp_l[(1 * 3 + nt) * 32 + lane]);
             const float2 sa = *reinterpret_cast<const float2 *>(sa_s + 8 * nt + 2 * q);
-            const float2 xa = *reinterpret_cast<const float2 *>(x0 + 8 * nt), xb2 = *reinterpret_cast<const float2 *>(x1 + 8 * nt);
+            const bool real = nt < 2 || q0;   // padding slots: no load (the next token's row belongs to another warp)
+            const float2 xa = real ? *reinterpret_cast<const float2 *>(x0 + 8 * nt) : make_float2(0.f, 0.f);
+            const float2 xb2 = real ? *reinterpret_cast<const float2 *>(x1 + 8 * nt) : make_float2(0.f, 0.f);
             u0[2 * nt] = fmaf(sa.x, p[0], xa.x), u0[2 * nt + 1] = fmaf(sa.y, p[1], xa.y);
             u1[2 * nt] = fmaf(sa.x, p[2], xb2.x), u1[2 * nt + 1] = fmaf(sa.y, p[3], xb2.y);
           }
