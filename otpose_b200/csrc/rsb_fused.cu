@@ -332,30 +332,30 @@ __global__ void __launch_bounds__(RTH, 2) rsb_level_kernel(const __grid_constant
     } else {
       // the block input x: fp32 NCHW -> 16-bit pixel-major.  Work item = (tile row, 16-pixel group, channel block);
       // 8 channels of a pixel become one 16-byte store; a half-warp reads 64 contiguous bytes per channel.
-      const int ncb = T.ch >> 3, items = A.rows * A.MT * ncb;
-      constexpr int U = 4;   // items per thread in flight (32 loads) before the first conversion
-      for (int it0 = warp * 2 + (lane >> 4); it0 < items; it0 += RNW * 2 * U) {
-        float v[U][8];
+      // half-warp = (tile row, 16-pixel group); its channel blocks four at a time (32 loads in flight per thread)
+      const int ncb = T.ch >> 3;
+      for (int it = warp * 2 + (lane >> 4); it < A.rows * A.MT; it += RNW * 2) {
+        const int j = it / A.MT, m = it - j * A.MT, r = tr0 - A.halo + j, p = 16 * m + (lane & 15);
+        const bool ok = r >= 0 && r < A.H && p < A.W;
+        const float *src = A.x + (size_t)b * A.x_bs + (size_t)(ok ? r : 0) * A.W + (ok ? p : 0);
+        uint8_t *dst = tile + j * rowb + (p + 1) * T.sp * 2;
+        __half *xdst = A.xplane + (((size_t)b * A.H + r) * A.W + p) * A.cinp;
+        for (int cb0 = 0; cb0 < ncb; cb0 += 4) {
+          float v[4][8];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int it = it0 + u * RNW * 2;
-          const int cb = it % ncb, m = (it / ncb) % A.MT, j = it / (ncb * A.MT), r = tr0 - A.halo + j;
-          const int p = 16 * m + (lane & 15);
-          const bool ok = it < items && r >= 0 && r < A.H && p < A.W;
-          const float *src = A.x + (size_t)b * A.x_bs + (size_t)(8 * cb) * P + (size_t)r * A.W + p;
+          for (int u = 0; u < 4; ++u)
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[u][e] = (ok && 8 * cb + e < A.cin) ? __ldg(src + (size_t)e * P) : 0.f;
-        }
+            for (int e = 0; e < 8; ++e) {
+              const int c = 8 * (cb0 + u) + e;
+              v[u][e] = (ok && c < A.cin) ? __ldg(src + (size_t)c * P) : 0.f;
+            }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int it = it0 + u * RNW * 2;
-          if (it >= items) continue;
-          const int cb = it % ncb, m = (it / ncb) % A.MT, j = it / (ncb * A.MT), r = tr0 - A.halo + j;
-          const int p = 16 * m + (lane & 15);
-          const uint4 h = tc::pack16x8<true>(v[u]);
-          *reinterpret_cast<uint4 *>(tile + j * rowb + ((p + 1) * T.sp + 8 * cb) * 2) = h;
-          if (A.write_x && p < A.W && r < A.H)   // 16-bit pixel-major copy of x for level 8
-            *reinterpret_cast<uint4 *>(A.xplane + (((size_t)b * A.H + r) * A.W + p) * A.cinp + 8 * cb) = h;
+          for (int u = 0; u < 4; ++u) {
+            if (cb0 + u >= ncb) continue;
+            const uint4 h = tc::pack16x8<true>(v[u]);
+            *reinterpret_cast<uint4 *>(dst + 16 * (cb0 + u)) = h;
+            if (A.write_x && ok) *reinterpret_cast<uint4 *>(xdst + 8 * (cb0 + u)) = h;   // 16-bit copy of x for level 8
+          }
         }
       }
       for (int i = threadIdx.x; i < A.rows * (T.sp >> 3) * 2; i += RTH) {   // pixels 0 and BWP - 1 (16 MT + 1)
