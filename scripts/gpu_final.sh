@@ -11,3 +11,8 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:
 python scripts/step_share.py gpurun_out/${tag}_launches.csv > gpurun_out/${tag}_step_share.txt 2>&1; head -30 gpurun_out/${tag}_step_share.txt
 timeout 400 ncu --set full --clock-control none --import-source on -k 'regex:tc_back|tc_front1|tc_apply|gram_project' --launch-skip 8 -c 4 -f -o gpurun_out/${tag}_prof_blocks \
   python scripts/prof_block.py 32 6912 1 4 > gpurun_out/${tag}_prof_blocks.log 2>&1; echo "ncu full rc=$?"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:flow_encoder -s 3 -c 1 -f -o gpurun_out/${tag}_prof_flow \
+  python scripts/prof_flow.py > gpurun_out/${tag}_prof_flow.log 2>&1; echo "ncu flow rc=$?"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:rsb_level -s 270 -c 18 -f -o gpurun_out/${tag}_prof_rsb \
+  python scripts/prof_rsb.py > gpurun_out/${tag}_prof_rsb.log 2>&1; echo "ncu rsb rc=$?"
+timeout 100 python scripts/prof_flow.py > gpurun_out/${tag}_time_flow.log 2>&1; timeout 100 python scripts/prof_rsb.py > gpurun_out/${tag}_time_rsb.log 2>&1; cat gpurun_out/${tag}_time_flow.log gpurun_out/${tag}_time_rsb.log

@@ -76,11 +76,46 @@ if os.path.exists(rep):
                 + out + "```\n")
     print("wrote", f"{rnd}_ncu_summary.md")
 
+# ---- the round-2 kernels outside the C = 136 blocks: flow encoder (one cluster launch), RSB level kernels
+for name, what in (("flow", "the C = 17 flow encoder, 32 clips x 6912 tokens, 6 blocks in one cluster launch (`scripts/prof_flow.py`)"),
+                   ("rsb", "offset_mask_combine_conv (51 -> 32 -> 32, 18 level launches) at 32 clips x 96 x 72 (`scripts/prof_rsb.py`)")):
+    rep2 = os.path.join(G, f"{tag}_prof_{name}.ncu-rep")
+    if not os.path.exists(rep2):
+        continue
+    raw = subprocess.run(["ncu", "-i", rep2, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr = rows[0]
+    keys = ["gpu__time_duration.sum", "launch__grid_size", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
+            "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+            "sm__warps_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
+            "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio"]
+    with open(os.path.join(P, f"{rnd}_ncu_{name}.md"), "w") as f:
+        f.write(f"# {rnd} ncu `--set full --clock-control none`: {what}\n\n"
+                "Times under ncu are cold-cache and serialised; the graph-replay times are in the log below.\n\n```\n")
+        for r in rows[2:]:
+            d = dict(zip(hdr, r))
+            f.write(d.get("Kernel Name", "")[:70] + "\n")
+            for k in keys:
+                if k in d:
+                    f.write(f"  {k:86s} {d[k]}\n")
+        for lg in (f"{tag}_time_{name}.log",):
+            if os.path.exists(os.path.join(G, lg)):
+                f.write("\n" + open(os.path.join(G, lg)).read())
+        f.write("```\n")
+    print("wrote", f"{rnd}_ncu_{name}.md")
+
 # ---- SASS opcode histogram of the built objects (Blackwell-nativeness in-tree)
-ops = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "LDGSTS", "SYNCS", "ELECT"]
+ops = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "LDGSTS", "SYNCS", "ELECT", "HMMA", "LDSM", "MOVM", "UCGABAR_ARV"]
 lines = ["tcgen05 / TMA opcode counts per object (cuobjdump -sass otpose_b200/build/*.o)",
          "UTCHMMA = tcgen05.mma kind::f16, LDTM = tcgen05.ld, UTMALDG / UTMASTG = cp.async.bulk.tensor load / store,",
-         "UBLKCP = cp.async.bulk (non-tensor), UTCBAR = tcgen05.commit, LDGSTS = cp.async", "",
+         "UBLKCP = cp.async.bulk (non-tensor), UTCBAR = tcgen05.commit, LDGSTS = cp.async; HMMA / LDSM / MOVM = mma.sync / ldmatrix /",
+         "movmatrix of the narrow-channel kernels (block_flow, rsb_fused), UCGABAR_ARV = cluster barrier arrive", "",
          f"{'object':22s}" + "".join(f"{o:>9s}" for o in ops)]
 for obj in sorted(glob.glob(os.path.join(ROOT, "otpose_b200", "build", "*.o"))):
     sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
