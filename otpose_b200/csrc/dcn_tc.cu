@@ -242,6 +242,15 @@ tc_dcn_fused_kernel(const uint8_t *__restrict__ wimg, const float *__restrict__ 
     // ---- combine the three thread thirds (exchange buffer aliases the dead im2col taps): every
     //      thread publishes its 17 partial sums, then third q reduces and stores outputs q, q+3, ... ----
     float *ex = reinterpret_cast<float *>(as);
+    // the running sums this thread adds to (launches 2..10 of a forward): all six loads in flight across the
+    // exchange barrier -- read one by one next to their stores they were six serialised round trips per tile
+    // (17 % of the kernel's stall samples)
+    float prev[(kJ + 2) / 3];
+#pragma unroll
+    for (int i = 0; i < (kJ + 2) / 3; ++i) {
+      const int o = third + 3 * i;
+      prev[i] = (live && accumulate && o < kJ) ? out[((size_t)b * kJ + o) * P + p] : 0.f;
+    }
 #pragma unroll
     for (int o = 0; o < kJ; ++o) ex[(third * kJ + o) * kTM + tok] = acc[o];
     tc_fence_before();
@@ -253,8 +262,7 @@ tc_dcn_fused_kernel(const uint8_t *__restrict__ wimg, const float *__restrict__ 
         if (o < kJ) {
           const float v = ex[o * kTM + tok] + ex[(kJ + o) * kTM + tok] + ex[(2 * kJ + o) * kTM + tok] +
                           (dcn_b ? __ldg(dcn_b + o) : 0.f);
-          float *dst = out + ((size_t)b * kJ + o) * P + p;
-          *dst = accumulate ? fmaf(alpha, v, *dst) : alpha * v;
+          out[((size_t)b * kJ + o) * P + p] = fmaf(alpha, v, prev[i]);
         }
       }
     }

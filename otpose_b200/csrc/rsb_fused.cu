@@ -471,28 +471,35 @@ __global__ void rsb_pack_kernel(const PackArgs A) {
 
 // ------------------------------------------------------------------------------------------ levels
 // planes of the 16-bit scratch
-enum { PL_S0 = 0, PL_S1, PL_S2, PL_S3, PL_11, PL_21, PL_22, PL_31, PL_32, PL_33, PL_41, PL_42, PL_43, PL_44, PL_COUNT };
+// ... 14 maps in 6 slots: a map takes the slot of one whose last reader is an EARLIER level (a level's CTAs read halo
+// rows that other CTAs of the same launch must not be overwriting).  Live ranges (written at level -> last read):
+// S0 0-1, S1 0-2, S2 0-3, S3 0-4, 11 1-8, 21 2-3, 22 3-8, 31 3-4, 32 4-5, 41 4-5, 33 5-8, 42 5-6, 43 6-7, 44 7-8.
+enum {
+  PL_S0 = 0, PL_S1 = 1, PL_S2 = 2, PL_S3 = 3, PL_11 = 4,
+  PL_21 = 0, PL_22 = 1, PL_31 = 5, PL_32 = 0, PL_41 = 2, PL_33 = 3, PL_42 = 5, PL_43 = 0, PL_44 = 2,
+  PL_COUNT = 6
+};
 struct LevelOp {
   int unit, k, plane;
   std::vector<int> in;   // input planes (-1 = x)
 };
+static std::vector<std::vector<LevelOp>> make_levels(bool has_ds) {
+  return {
+      {{0, 1, PL_S0, {-1}}, {1, 1, PL_S1, {-1}}, {2, 1, PL_S2, {-1}}, {3, 1, PL_S3, {-1}}},
+      {{4, 3, PL_11, {PL_S0}}},
+      {{5, 3, PL_21, {PL_S1, PL_11}}},
+      {{6, 3, PL_22, {PL_21}}, {7, 3, PL_31, {PL_S2, PL_21}}},
+      {{8, 3, PL_32, {PL_31, PL_22}}, {10, 3, PL_41, {PL_S3, PL_31}}},
+      {{9, 3, PL_33, {PL_32}}, {11, 3, PL_42, {PL_41, PL_32}}},
+      {{12, 3, PL_43, {PL_42, PL_33}}},
+      {{13, 3, PL_44, {PL_43}}},
+      {{14, 1, -1, has_ds ? std::vector<int>{PL_11, PL_22, PL_33, PL_44, -2} : std::vector<int>{PL_11, PL_22, PL_33, PL_44}}},
+  };
+}
 static const std::vector<std::vector<LevelOp>> &rsb_levels(bool has_ds) {
-  static std::vector<std::vector<LevelOp>> lv[2];
-  auto &L = lv[has_ds ? 1 : 0];
-  if (L.empty()) {
-    L = {
-        {{0, 1, PL_S0, {-1}}, {1, 1, PL_S1, {-1}}, {2, 1, PL_S2, {-1}}, {3, 1, PL_S3, {-1}}},
-        {{4, 3, PL_11, {PL_S0}}},
-        {{5, 3, PL_21, {PL_S1, PL_11}}},
-        {{6, 3, PL_22, {PL_21}}, {7, 3, PL_31, {PL_S2, PL_21}}},
-        {{8, 3, PL_32, {PL_31, PL_22}}, {10, 3, PL_41, {PL_S3, PL_31}}},
-        {{9, 3, PL_33, {PL_32}}, {11, 3, PL_42, {PL_41, PL_32}}},
-        {{12, 3, PL_43, {PL_42, PL_33}}},
-        {{13, 3, PL_44, {PL_43}}},
-        {{14, 1, -1, has_ds ? std::vector<int>{PL_11, PL_22, PL_33, PL_44, -2} : std::vector<int>{PL_11, PL_22, PL_33, PL_44}}},
-    };
-  }
-  return L;
+  // function-local statics: initialised once, thread-safe (a process may drive several GPUs from several threads)
+  static const std::vector<std::vector<LevelOp>> with_ds = make_levels(true), without = make_levels(false);
+  return has_ds ? with_ds : without;
 }
 
 // shared-memory plan of one level; false if even a one-row tile does not fit
