@@ -64,6 +64,36 @@ def test_shape_queries_and_unsupported_widths():
     assert lib.otp_final_layer_fusion_sum(None, 1, 1, None, None, 5, 0, 48, 17, 64, None, None, None, None) == 0
 
 
+def test_flow_encoder_and_rsb_block_queries():
+    """Round-2 entry points (one-launch flow encoder, RSB level kernels): what is built / refused, workspace
+    sizes, argument handling before any CUDA call."""
+    lib = _lib.load()
+    # flow encoder: C = 17 / one head, <= 8 blocks, up to 8 x 1728 tokens per clip
+    assert lib.otp_flow_encoder_supported(17, 1, 96 * 72, 6) == 1
+    assert lib.otp_flow_encoder_supported(17, 1, 128 * 96, 6) == 1
+    assert lib.otp_flow_encoder_supported(17, 1, 35, 1) == 1
+    assert lib.otp_flow_encoder_supported(136, 2, 96 * 72, 6) == 0
+    assert lib.otp_flow_encoder_supported(17, 1, 8 * 1728 + 1, 6) == 0
+    assert lib.otp_flow_encoder_supported(17, 1, 96 * 72, 9) == 0
+    assert lib.otp_flow_encoder_workspace_bytes(32, 6912) >= 32 * 6912 * 17 * 4      # fp32 scramble buffer
+    assert lib.otp_flow_encoder_workspace_bytes(0, 6912) == 0
+    assert lib.otp_flow_encoder_forward(None, 6, None, None, 0, None, 1, 6912, None, 0, None) == 1   # no block table
+    # RSB blocks: the three widths of the head (and the 128 x 96 maps of BASELINE config 5); maps wider than 96 are
+    # refused (the caller falls back to the per-conv kernels)
+    for cin, planes in ((17, 17), (51, 32), (32, 32)):
+        assert lib.otp_rsb_block_supported(cin, planes, 96, 72) == 1
+        assert lib.otp_rsb_block_supported(cin, planes, 128, 96) == 1
+        assert lib.otp_rsb_block_supported(cin, planes, 9, 7) == 1
+        assert lib.otp_rsb_block_pack_bytes(cin, planes, 1) > lib.otp_rsb_block_pack_bytes(cin, planes, 0) > 0
+    assert lib.otp_rsb_block_supported(51, 32, 96, 104) == 0
+    assert lib.otp_rsb_block_supported(128, 32, 96, 72) == 0
+    # six 16-bit planes of cp channels + the 16-bit copy of x
+    assert lib.otp_rsb_block_workspace_bytes(32, 51, 32, 96, 72) >= 32 * 96 * 72 * 2 * (6 * 24 + 56)
+    assert lib.otp_rsb_block_forward(None, None, 0, None, 0, 1, 128, 32, 1, 96, 72, None, 0, None) == 2   # unsupported
+    assert lib.otp_rsb_block_forward(None, None, 0, None, 0, 0, 51, 32, 1, 96, 72, None, 0, None) == 0    # empty batch
+    assert lib.otp_rsb_block_forward(None, None, 0, None, 0, 1, 51, 32, 1, 96, 72, None, 0, None) == 1    # null pointers
+
+
 def manifest():
     with open(os.path.join(ROOT, "tests", "golden", "state_dict_manifest.json")) as f:
         return json.load(f)
