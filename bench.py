@@ -524,12 +524,80 @@ def run_b200(args):
                 line["full_inference"] = full_inference(args, model, dev, precision)
             except Exception as e:      # the secondary leg must never cost the headline line
                 line["full_inference"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+        if world == 1 and not args.no_full_inference and (H, W) == (96, 72) and FRAMES == 5:
+            try:
+                line["window_assembly"] = window_assembly(args, dev)
+            except Exception as e:
+                line["window_assembly"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference(args.cpu_clips, 3, 1)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def window_assembly(args, dev):
+    """the input window assembly (cv2.warpAffine + ToTensor + Normalize + concat of the five frames
+    of every clip) as one launch on uint8 frames resident on the device: 32 clips x 5 frames, 384x288 crops out of
+    720p frames -> concat_input (32, 15, 384, 288) fp32.  HBM-bound; algorithmic bytes = the fp32 output + the uint8
+    source boxes.  CPU line beside it: the reference's own calls (cv2.warpAffine + torchvision transforms) when cv2
+    is importable on the box, else the NumPy oracle port."""
+    import time
+    import numpy as np
+    import torch
+    from otpose_b200.dataset import window as win
+    b, nfr, hs, ws = min(args.batch, 32), 8, 720, 1280
+    r = np.random.default_rng(4321)
+    frames = torch.from_numpy(r.integers(0, 256, (nfr, hs, ws, 3), dtype=np.uint8)).to(dev)
+    centers = np.stack([r.uniform(200, ws - 200, b), r.uniform(150, hs - 150, b)], 1).astype(np.float32)
+    sc = r.uniform(1.0, 2.6, b).astype(np.float32)                       # box height 200 .. 520 px
+    scales = np.stack([sc * 0.75, sc], 1)
+    fi = r.integers(0, nfr, (b, 5))
+    tr = np.stack([win.get_affine_transform(centers[i], scales[i], 0, (4 * W, 4 * H)) for i in range(b)])
+    fi_d, tr_d = torch.from_numpy(fi).to(dev), torch.from_numpy(tr).to(dev)
+    for _ in range(3):
+        out, _, _ = win.assemble_windows(frames, fi_d, tr_d, (4 * W, 4 * H), True)
+    n = 20
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        out, _, _ = win.assemble_windows(frames, fi_d, tr_d, (4 * W, 4 * H), True)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / n
+    out_bytes = out.numel() * 4
+    src_bytes = float(sum(5 * 3 * (200 * s[0]) * (200 * s[1]) for s in scales))
+    peaks = load_peaks()
+    res = {"config": f"{b} clips x 5 frames, {4 * H}x{4 * W} crops of {hs}x{ws} uint8 frames on the device -> "
+                     f"concat_input ({b},15,{4 * H},{4 * W}) fp32 (bit-exact with cv2.warpAffine + torchvision)",
+           "clips_per_s": b / (ms / 1e3), "ms_per_step": ms, "bound": "hbm",
+           "achieved": (out_bytes + src_bytes) / (ms / 1e3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+           "wire_bytes_per_clip": {"this (48 B transform + 20 B frame ids; frames shared)": 68, "reference (fp32 crops)": out_bytes // b}}
+    res["frac"] = res["achieved"] / res["peak"]
+    if not args.no_cpu_baseline:
+        nb = 4
+        try:
+            import cv2
+            import torchvision.transforms as T
+            tf = T.Compose([T.ToTensor(), T.Normalize(mean=win.MEAN, std=win.STD)])
+            fr = frames.cpu().numpy()
+            t0 = time.time()
+            for i in range(nb):
+                torch.cat([tf(cv2.warpAffine(cv2.cvtColor(fr[f], cv2.COLOR_BGR2RGB), tr[i], (4 * W, 4 * H), flags=cv2.INTER_LINEAR))
+                           for f in fi[i]], 0)
+            kind = "reference"
+        except ImportError:
+            from oracle import window_oracle as wo
+            fr = frames.cpu().numpy()
+            t0 = time.time()
+            for i in range(nb):
+                np.concatenate([wo.to_tensor_normalize(wo.warp_affine_u8(fr[f][:, :, ::-1], tr[i], (4 * W, 4 * H))) for f in fi[i]], 0)
+            kind = "port"
+        res["cpu_baseline"] = {"value": nb / (time.time() - t0), "unit": "clips/s", "cores": 1, "kind": kind,
+                               "sample": f"{nb} clips of the same workload, one host thread (a DataLoader worker)"}
+    return res
 
 
 def run_train(args):

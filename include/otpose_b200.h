@@ -259,6 +259,20 @@ int otp_conv_bn_fold(const float *weight, const float *bias, const float *gamma,
                      const float *running_mean, const float *running_var, float eps, int has_bn, int cout,
                      int per_out, float *weight_out, float *bias_out, otp_stream_t stream);
 
+/* f4: input window assembly, replaces dataset/PoseTrackDataset.py:389-406 (cv2.warpAffine of the
+ * clip's frames with the get_affine_transform matrix, ToTensor, Normalize) and the torch.cat of script/Common.py:347.
+ * frames: device uint8 (n_frames, src_h, src_w, 3) as cv2.imread returns them (frame_stride bytes apart);
+ * frame_index: device int32 (B, frames_per_clip) rows of `frames` in the order cur, prev, next, pprev, nnext;
+ * trans: device double (B, 6), the FORWARD 2x3 matrix of get_affine_transform(center, scale, 0, (out_w, out_h));
+ * swap_rb = 1: cv2.cvtColor(BGR2RGB) first (cfg color_rgb); mean3 / std3: HOST float[3].
+ * out: (B, 3 * frames_per_clip, out_h, out_w) fp32 = concat_input (may be NULL); out_bf16_nhwc: the same pixels as the
+ * (frames_per_clip * B, out_h, out_w, 3) bfloat16 channels-last batch of model/OTPose.py:317 (may be NULL).
+ * The warp is bit-exact with cv2.warpAffine(INTER_LINEAR, BORDER_CONSTANT 0); the fp32 output bit-exact with torchvision. */
+int otp_window_assemble(const unsigned char *frames, int n_frames, int src_h, int src_w, long long frame_stride,
+                        const int *frame_index, int frames_per_clip, const double *trans, int b, int out_h, int out_w,
+                        int swap_rb, const float *mean3, const float *std3, float *out, void *out_bf16_nhwc,
+                        otp_stream_t stream);
+
 /* a7, 16-bit modes: a whole RSB_BLOCK (model/RSB.py:26-103: conv_bn_relu1, the ten dense-connected 3x3
  * conv_bn_relu2_* convs, conv_bn_relu3 + skip / downsample + ReLU) in one launch -- two for the widest block -- with
  * every intermediate map in shared-memory row rings (csrc/rsb_fused.cu).  `weights` / `biases`: HOST arrays of 13

@@ -68,6 +68,7 @@ SIGNATURES = {
     "otp_conv2d_wgrad_workspace_bytes": (sz, [i32, i32, i32, i32, i32, i32]),
     "otp_conv2d_wgrad": (i32, [vp, i64, vp, i64, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, sz, vp]),
     "otp_conv_bn_fold": (i32, [vp, vp, vp, vp, vp, vp, f32, i32, i32, i32, vp, vp, vp]),
+    "otp_window_assemble": (i32, [vp, i32, i32, i32, i64, vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
     "otp_rsb_block_supported": (i32, [i32, i32, i32, i32]),
     "otp_rsb_block_pack_bytes": (sz, [i32, i32, i32]),
     "otp_rsb_block_pack": (i32, [vp, vp, i32, i32, i32, vp, sz, vp]),

@@ -74,7 +74,7 @@ inline bool set_max_smem(F *kernel, size_t bytes, const char *name) {
 enum KernelId {
   K_FINAL_PREDS = 0, K_MDCN, K_FUSION_SUM, K_FUSION_STACK, K_ADD_PE, K_UPSAMPLE, K_PYRAMID, K_CONV2D,
   K_BLOCK_FRONT, K_BLOCK_FOLD, K_BLOCK_APPLY, K_BLOCK_BACK, K_PACK, K_TC_FRONT, K_TC_APPLY, K_TC_BACK,
-  K_TC_CONV, K_MDCN_BWD, K_FINAL_LAYER, K_CONV_BWD, K_FLOW_ENCODER, K_RSB, K_COUNT
+  K_TC_CONV, K_MDCN_BWD, K_FINAL_LAYER, K_CONV_BWD, K_FLOW_ENCODER, K_RSB, K_WINDOW, K_COUNT
 };
 
 // RAII around one (or n) kernel launch(es) on `st`: counts them and, when

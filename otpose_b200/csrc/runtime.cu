@@ -33,7 +33,7 @@ std::vector<Record> g_pool;          // recycled event pairs
 const char *kNames[K_COUNT] = {"final_preds", "mdcn_fwd", "fusion_sum", "fusion_stack", "add_pos_embd",
                                "upsample_linear", "pyramid_conv1x1", "conv2d", "block_front", "block_fold",
                                "block_apply", "block_back", "pack", "tc_block_front", "tc_block_apply",
-                               "tc_block_back", "tc_offset_mask_dcn", "mdcn_bwd", "final_layer_sum", "conv2d_bwd", "flow_encoder", "rsb_block"};
+                               "tc_block_back", "tc_offset_mask_dcn", "mdcn_bwd", "final_layer_sum", "conv2d_bwd", "flow_encoder", "rsb_block", "window_assemble"};
 }  // namespace
 
 LaunchScope::LaunchScope(int id, cudaStream_t st, int nlaunch) : slot_(-1), st_(st) {
