@@ -14,7 +14,7 @@
 // the same operation order (no FMA contraction: __dmul_rn / __dadd_rn), the source position is the same FIXED-POINT
 // number (x 1024, + 16, >> 5: 1/32 pixel), the bilinear weights are the same 15-bit integers
 // ((32 - fy)(32 - fx) 32, ...), the pixel is (sum + 2^14) >> 15, BORDER_CONSTANT 0.  ToTensor / Normalize are the same
-// three fp32 operations (/ 255, - mean, / std; IEEE division).  One thread = one output pixel of one clip: the
+// three fp32 operations (/ 255, - mean, / std; IEEE division), tabulated per CTA for the 256 possible inputs.  One thread = one output pixel of one clip: the
 // fixed-point position is computed once and used for all five frames and three channels; fp32 NCHW stores are
 // coalesced along x; an optional second output is the 16-bit channels-last (5B, H, W, 3) batch the backbone
 // drop-in consumes (model/OTPose.py:317: cat(x.split(3, dim=1), 0) -> frame-major).
@@ -37,8 +37,20 @@ struct WindowArgs {
   __nv_bfloat16 *out16;
 };
 
+constexpr int kWinRows = 8;   // output rows per CTA: amortises the normalisation table and the per-column constants
+
 __global__ void __launch_bounds__(128) window_kernel(const WindowArgs A) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+  // ToTensor + Normalize of a uint8 has 256 possible results per channel: the three IEEE operations are evaluated
+  // once per table entry (bit-exact by construction) instead of two fp32 divisions per output value
+  __shared__ float lut[3][256];
+  for (int e = threadIdx.x; e < 3 * 256; e += blockDim.x) {
+    const int c = e >> 8, u = e & 255;
+    const float mean = c == 0 ? A.mean[0] : (c == 1 ? A.mean[1] : A.mean[2]);
+    const float sd = c == 0 ? A.stdv[0] : (c == 1 ? A.stdv[1] : A.stdv[2]);
+    lut[c][u] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)u, 255.0f), mean), sd);
+  }
+  __syncthreads();
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.z;
   if (x >= A.out_w) return;
   // ---- cv::warpAffine: invert the 2x3 matrix (double, same operation order as imgwarp.cpp) ----
   const double *T = A.trans + (size_t)b * 6;
@@ -55,36 +67,46 @@ __global__ void __launch_bounds__(128) window_kernel(const WindowArgs A) {
   // ---- fixed-point source position: AB_BITS = 10, INTER_BITS = 5, round_delta = 16 ----
   const int adelta = __double2int_rn(__dmul_rn(__dmul_rn(m0, (double)x), 1024.0));
   const int bdelta = __double2int_rn(__dmul_rn(__dmul_rn(m3, (double)x), 1024.0));
-  const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m1, (double)y), b1), 1024.0)) + 16;
-  const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m4, (double)y), b2), 1024.0)) + 16;
-  const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
-  const int sx = min(max(X >> 5, -32768), 32767), sy = min(max(Y >> 5, -32768), 32767);   // saturate_cast<short>
-  const int fx = X & 31, fy = Y & 31;
-  const int w00 = (32 - fy) * (32 - fx) * 32, w01 = (32 - fy) * fx * 32, w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
-  const bool x0 = sx >= 0 && sx < A.src_w, x1 = sx + 1 >= 0 && sx + 1 < A.src_w;
-  const bool y0 = sy >= 0 && sy < A.src_h, y1 = sy + 1 >= 0 && sy + 1 < A.src_h;
-  const size_t P = (size_t)A.out_h * A.out_w, px = (size_t)y * A.out_w + x;
-  for (int f = 0; f < A.nf; ++f) {
-    const int fi = A.frame_index[b * A.nf + f];
-    const unsigned char *src = A.frames + (size_t)min(max(fi, 0), A.n_frames - 1) * A.frame_stride;
-    const unsigned char *r0 = src + ((size_t)(y0 ? sy : 0) * A.src_w) * 3, *r1 = src + ((size_t)(y1 ? sy + 1 : 0) * A.src_w) * 3;
+  const size_t P = (size_t)A.out_h * A.out_w;
+  const int ci0 = A.swap_rb ? 2 : 0, ci2 = A.swap_rb ? 0 : 2;   // cv2.cvtColor(BGR2RGB) before the warp == channel choice after it
+  const int y_end = min(A.out_h, (int)(blockIdx.y + 1) * kWinRows);
+  for (int y = blockIdx.y * kWinRows; y < y_end; ++y) {
+    const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m1, (double)y), b1), 1024.0)) + 16;
+    const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m4, (double)y), b2), 1024.0)) + 16;
+    const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
+    const int sx = min(max(X >> 5, -32768), 32767), sy = min(max(Y >> 5, -32768), 32767);   // saturate_cast<short>
+    const int fx = X & 31, fy = Y & 31;
+    const bool x0 = sx >= 0 && sx < A.src_w, x1 = sx + 1 >= 0 && sx + 1 < A.src_w;
+    const bool y0 = sy >= 0 && sy < A.src_h, y1 = sy + 1 >= 0 && sy + 1 < A.src_h;
+    // border taps (BORDER_CONSTANT 0) get weight 0 and a clamped address
+    const int w00 = (y0 && x0) ? (32 - fy) * (32 - fx) * 32 : 0, w01 = (y0 && x1) ? (32 - fy) * fx * 32 : 0;
+    const int w10 = (y1 && x0) ? fy * (32 - fx) * 32 : 0, w11 = (y1 && x1) ? fy * fx * 32 : 0;
+    const size_t o0 = ((size_t)(y0 ? sy : 0) * A.src_w) * 3, o1 = ((size_t)(y1 ? sy + 1 : 0) * A.src_w) * 3;
     const int c0 = (x0 ? sx : 0) * 3, c1 = (x1 ? sx + 1 : 0) * 3;
-    float v[3];
+    const size_t px = (size_t)y * A.out_w + x;
+    for (int f = 0; f < A.nf; ++f) {
+      const int fi = A.frame_index[b * A.nf + f];
+      const unsigned char *src = A.frames + (size_t)min(max(fi, 0), A.n_frames - 1) * A.frame_stride;
+      const unsigned char *r0 = src + o0, *r1 = src + o1;
+      int t[4][3];   // the four taps' three bytes: all twelve loads in flight
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const int sc = A.swap_rb ? 2 - c : c;   // cv2.cvtColor(BGR2RGB) before the warp == channel choice after it
-      const int p00 = (y0 && x0) ? r0[c0 + sc] : 0, p01 = (y0 && x1) ? r0[c1 + sc] : 0;
-      const int p10 = (y1 && x0) ? r1[c0 + sc] : 0, p11 = (y1 && x1) ? r1[c1 + sc] : 0;
-      const int u = (p00 * w00 + p01 * w01 + p10 * w10 + p11 * w11 + (1 << 14)) >> 15;
-      // ToTensor: uint8 -> float32 / 255;  Normalize: (x - mean) / std
-      v[c] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)u, 255.0f), A.mean[c]), A.stdv[c]);
-      if (A.out) A.out[((size_t)b * (3 * A.nf) + 3 * f + c) * P + px] = v[c];
-    }
-    if (A.out16) {
-      __nv_bfloat16 *d = A.out16 + (((size_t)f * A.b + b) * P + px) * 3;
-      d[0] = __float2bfloat16_rn(v[0]);
-      d[1] = __float2bfloat16_rn(v[1]);
-      d[2] = __float2bfloat16_rn(v[2]);
+      for (int c = 0; c < 3; ++c) t[0][c] = r0[c0 + c], t[1][c] = r0[c1 + c], t[2][c] = r1[c0 + c], t[3][c] = r1[c1 + c];
+      float v[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int sc = c == 0 ? ci0 : (c == 1 ? 1 : ci2);
+        const int s0 = sc == 0 ? t[0][0] : (sc == 1 ? t[0][1] : t[0][2]), s1 = sc == 0 ? t[1][0] : (sc == 1 ? t[1][1] : t[1][2]);
+        const int s2 = sc == 0 ? t[2][0] : (sc == 1 ? t[2][1] : t[2][2]), s3 = sc == 0 ? t[3][0] : (sc == 1 ? t[3][1] : t[3][2]);
+        const int u = (s0 * w00 + s1 * w01 + s2 * w10 + s3 * w11 + (1 << 14)) >> 15;
+        v[c] = lut[c][u];   // ToTensor: uint8 -> float32 / 255;  Normalize: (x - mean) / std
+        if (A.out) A.out[((size_t)b * (3 * A.nf) + 3 * f + c) * P + px] = v[c];
+      }
+      if (A.out16) {
+        __nv_bfloat16 *d = A.out16 + (((size_t)f * A.b + b) * P + px) * 3;
+        d[0] = __float2bfloat16_rn(v[0]);
+        d[1] = __float2bfloat16_rn(v[1]);
+        d[2] = __float2bfloat16_rn(v[2]);
+      }
     }
   }
 }
@@ -112,6 +134,10 @@ extern "C" int otp_window_assemble(const unsigned char *frames, int n_frames, in
   A.out = out, A.out16 = static_cast<__nv_bfloat16 *>(out_bf16_nhwc);
   cudaStream_t st = (cudaStream_t)stream;
   LaunchScope ls(K_WINDOW, st);
-  window_kernel<<<dim3(ceil_div(out_w, 128), out_h, b), 128, 0, st>>>(A);
+  // threads per CTA: the candidate that pads the row least (288 = 3 x 96)
+  int bs = 128;
+  for (int c : {96, 64})
+    if (ceil_div(out_w, c) * c < ceil_div(out_w, bs) * bs) bs = c;
+  window_kernel<<<dim3(ceil_div(out_w, bs), ceil_div(out_h, kWinRows), b), bs, 0, st>>>(A);
   return check_launch("window_kernel");
 }
