@@ -299,9 +299,22 @@ def full_inference(args, model, dev, precision):
     net = net.eval().to(dev)
     fl_w, fl_b = net.final_layer.weight.detach().float(), net.final_layer.bias.detach().float()
     folded = net.fold(dtype=torch.bfloat16, memory_format=torch.channels_last)
-    g = torch.Generator().manual_seed(1235)
-    images = torch.randn((FRAMES * b, 3, 4 * H, 4 * W), generator=g).to(dev).to(torch.bfloat16) \
+    # the step starts from uint8 video frames on the device: the window assembly kernel writes the
+    # backbone graph's static bf16 channels-last input
+    import numpy as np
+    from otpose_b200.dataset import window as win
+    rr = np.random.default_rng(1235)
+    nfr, hs, ws = 8, 720, 1280
+    frames = torch.from_numpy(rr.integers(0, 256, (nfr, hs, ws, 3), dtype=np.uint8)).to(dev)
+    sc = rr.uniform(1.0, 2.6, b).astype(np.float32)
+    tr = torch.from_numpy(np.stack([win.get_affine_transform(
+        np.array([rr.uniform(200, ws - 200), rr.uniform(150, hs - 150)], np.float32), np.array([s * 0.75, s], np.float32), 0,
+        (4 * W, 4 * H)) for s in sc])).to(dev)
+    fidx = torch.from_numpy(rr.integers(0, nfr, (b, FRAMES))).to(dev)
+    images = torch.empty((FRAMES * b, 3, 4 * H, 4 * W), dtype=torch.bfloat16, device=dev) \
         .contiguous(memory_format=torch.channels_last)
+    window = lambda: win.assemble_windows(frames, fidx, tr, (4 * W, 4 * H), True, fp32=False, out16=images)   # noqa: E731
+    window()
     margin = syn.synth_margin(b, frames=FRAMES).to(dev)
     center, scale = (torch.from_numpy(a).to(dev) for a in syn.synth_center_scale(b))
     with torch.no_grad():
@@ -317,6 +330,7 @@ def full_inference(args, model, dev, precision):
         return heatmap.final_preds_cuda(out, center, scale)
 
     def step():
+        window()
         graph.replay()
         return head(feats)
 
@@ -336,12 +350,14 @@ def full_inference(args, model, dev, precision):
     ms_full = timed(step, n)
     ms_backbone = timed(graph.replay, n)
     ms_head = timed(lambda: head(feats), n)
+    ms_window = timed(window, n)
     assert bool(torch.isfinite(r["preds"]).all())
     return {"config": f"full OTPose inference: HRNet-W48 backbone (cuDNN, Conv+BN folded, channels-last bf16, CUDA "
                       f"graph; random init) + temporal head ({precision} operands, HRNet.final_layer fused into the "
-                      f"head) + get_final_preds, {b} clips x {FRAMES} frames of {4 * H}x{4 * W} synthetic images, 1 GPU",
+                      f"head) + get_final_preds, {b} clips x {FRAMES} frames cropped to {4 * H}x{4 * W} out of {hs}x{ws} uint8 "
+                      f"synthetic video frames on the device by the window-assembly kernel, 1 GPU",
             "clips_per_s": round(b / (ms_full * 1e-3), 1), "ms_per_step": round(ms_full, 3),
-            "backbone_ms": round(ms_backbone, 3), "head_ms": round(ms_head, 3),
+            "window_ms": round(ms_window, 3), "backbone_ms": round(ms_backbone, 3), "head_ms": round(ms_head, 3),
             "head_share_of_step": round(ms_head / (ms_backbone + ms_head), 4), "steps": n,
             "backbone_tflops": round(353.07e9 * b * (H * W) / T / (ms_backbone * 1e-3) / 1e12, 1),
             "note": "backbone = library (cuDNN) code, BASELINE.md section 3: 353 GFLOP/clip; head = this library"}

@@ -80,10 +80,12 @@ def get_affine_transform(center, scale, rot, output_size, shift=np.array([0, 0],
 
 
 def assemble_windows(frames, frame_index, trans, image_size, color_rgb=True, margin=None, fp32=True, bf16_nhwc=False,
-                     mean=MEAN, std=STD):
+                     mean=MEAN, std=STD, out=None, out16=None):
     """frames: ``(F, Hs, Ws, 3)`` uint8 CUDA tensor in ``cv2.imread`` (BGR) order; frame_index: ``(B, 5)`` integers --
     rows of ``frames`` for cur, prev, next, pprev, nnext (3 or 7 columns for the config-5 frame windows); trans:
     ``(B, 2, 3)`` float64 (``get_affine_transform(center, scale, 0, image_size)`` per clip); image_size ``(W, H)``.
+
+    ``out`` / ``out16``: preallocated outputs to fill (a CUDA-graph's static input buffer, for instance).
 
     Returns ``(concat_input (B, 3 * frames, H, W) fp32 | None, images (frames * B, 3, H, W) bf16 channels-last | None,
     margin (B, 4) int64 on the device | None)``."""
@@ -102,10 +104,19 @@ def assemble_windows(frames, frame_index, trans, image_size, color_rgb=True, mar
     if nf not in (3, 5, 7):
         raise NotImplementedError(f"frame window of {nf} not built (3, 5 or 7)")
     w, h = int(image_size[0]), int(image_size[1])
-    out = torch.empty((b, 3 * nf, h, w), dtype=torch.float32, device=dev) if fp32 else None
-    out16 = torch.empty((nf * b, 3, h, w), dtype=torch.bfloat16, device=dev).contiguous(
-        memory_format=torch.channels_last) if bf16_nhwc else None
-    if not fp32 and not bf16_nhwc:
+    if out is not None:
+        if out.shape != (b, 3 * nf, h, w) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != dev:
+            raise ValueError("out must be a contiguous (B, 3 * frames, H, W) float32 tensor on the frames' device")
+    elif fp32:
+        out = torch.empty((b, 3 * nf, h, w), dtype=torch.float32, device=dev)
+    if out16 is not None:
+        if (out16.shape != (nf * b, 3, h, w) or out16.dtype != torch.bfloat16 or out16.device != dev
+                or not out16.is_contiguous(memory_format=torch.channels_last)):
+            raise ValueError("out16 must be a channels-last (frames * B, 3, H, W) bfloat16 tensor on the frames' device")
+    elif bf16_nhwc:
+        out16 = torch.empty((nf * b, 3, h, w), dtype=torch.bfloat16, device=dev).contiguous(
+            memory_format=torch.channels_last)
+    if out is None and out16 is None:
         raise ValueError("nothing to produce")
     lib = _lib.load()
     mean3, std3 = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
