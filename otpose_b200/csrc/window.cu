@@ -39,6 +39,7 @@ struct WindowArgs {
 
 constexpr int kWinRows = 8;   // output rows per CTA: amortises the normalisation table and the per-column constants
 
+template <int NF>
 __global__ void __launch_bounds__(128) window_kernel(const WindowArgs A) {
   // ToTensor + Normalize of a uint8 has 256 possible results per channel: the three IEEE operations are evaluated
   // once per table entry (bit-exact by construction) instead of two fp32 divisions per output value
@@ -84,22 +85,27 @@ __global__ void __launch_bounds__(128) window_kernel(const WindowArgs A) {
     const size_t o0 = ((size_t)(y0 ? sy : 0) * A.src_w) * 3, o1 = ((size_t)(y1 ? sy + 1 : 0) * A.src_w) * 3;
     const int c0 = (x0 ? sx : 0) * 3, c1 = (x1 ? sx + 1 : 0) * 3;
     const size_t px = (size_t)y * A.out_w + x;
-    for (int f = 0; f < A.nf; ++f) {
-      const int fi = A.frame_index[b * A.nf + f];
+    // all taps of all NF frames in flight (12 byte loads per frame) before the first use
+    int t[NF][4][3];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      const int fi = A.frame_index[b * NF + f];
       const unsigned char *src = A.frames + (size_t)min(max(fi, 0), A.n_frames - 1) * A.frame_stride;
       const unsigned char *r0 = src + o0, *r1 = src + o1;
-      int t[4][3];   // the four taps' three bytes: all twelve loads in flight
 #pragma unroll
-      for (int c = 0; c < 3; ++c) t[0][c] = r0[c0 + c], t[1][c] = r0[c1 + c], t[2][c] = r1[c0 + c], t[3][c] = r1[c1 + c];
+      for (int c = 0; c < 3; ++c) t[f][0][c] = r0[c0 + c], t[f][1][c] = r0[c1 + c], t[f][2][c] = r1[c0 + c], t[f][3][c] = r1[c1 + c];
+    }
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
       float v[3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const int sc = c == 0 ? ci0 : (c == 1 ? 1 : ci2);
-        const int s0 = sc == 0 ? t[0][0] : (sc == 1 ? t[0][1] : t[0][2]), s1 = sc == 0 ? t[1][0] : (sc == 1 ? t[1][1] : t[1][2]);
-        const int s2 = sc == 0 ? t[2][0] : (sc == 1 ? t[2][1] : t[2][2]), s3 = sc == 0 ? t[3][0] : (sc == 1 ? t[3][1] : t[3][2]);
+        const int s0 = sc == 0 ? t[f][0][0] : (sc == 1 ? t[f][0][1] : t[f][0][2]), s1 = sc == 0 ? t[f][1][0] : (sc == 1 ? t[f][1][1] : t[f][1][2]);
+        const int s2 = sc == 0 ? t[f][2][0] : (sc == 1 ? t[f][2][1] : t[f][2][2]), s3 = sc == 0 ? t[f][3][0] : (sc == 1 ? t[f][3][1] : t[f][3][2]);
         const int u = (s0 * w00 + s1 * w01 + s2 * w10 + s3 * w11 + (1 << 14)) >> 15;
         v[c] = lut[c][u];   // ToTensor: uint8 -> float32 / 255;  Normalize: (x - mean) / std
-        if (A.out) A.out[((size_t)b * (3 * A.nf) + 3 * f + c) * P + px] = v[c];
+        if (A.out) A.out[((size_t)b * (3 * NF) + 3 * f + c) * P + px] = v[c];
       }
       if (A.out16) {
         __nv_bfloat16 *d = A.out16 + (((size_t)f * A.b + b) * P + px) * 3;
@@ -121,7 +127,7 @@ extern "C" int otp_window_assemble(const unsigned char *frames, int n_frames, in
                                    const double *trans, int b, int out_h, int out_w, int swap_rb, const float *mean3,
                                    const float *std3, float *out, void *out_bf16_nhwc, otp_stream_t stream) {
   OTP_REQUIRE(b >= 0 && n_frames > 0 && src_h > 0 && src_w > 0 && out_h > 0 && out_w > 0);
-  OTP_REQUIRE(frames_per_clip >= 1 && frames_per_clip <= 7 && out_h <= 65535 && b <= 65535);
+  OTP_REQUIRE((frames_per_clip == 3 || frames_per_clip == 5 || frames_per_clip == 7) && out_h <= 65535 && b <= 65535);
   OTP_REQUIRE(src_h <= 32767 && src_w <= 32767 && frame_stride >= (long long)src_h * src_w * 3);
   OTP_REQUIRE(mean3 != nullptr && std3 != nullptr);
   if (b == 0) return OTP_OK;
@@ -138,6 +144,9 @@ extern "C" int otp_window_assemble(const unsigned char *frames, int n_frames, in
   int bs = 128;
   for (int c : {96, 64})
     if (ceil_div(out_w, c) * c < ceil_div(out_w, bs) * bs) bs = c;
-  window_kernel<<<dim3(ceil_div(out_w, bs), ceil_div(out_h, kWinRows), b), bs, 0, st>>>(A);
+  const dim3 grid(ceil_div(out_w, bs), ceil_div(out_h, kWinRows), b);
+  if (frames_per_clip == 5) window_kernel<5><<<grid, bs, 0, st>>>(A);
+  else if (frames_per_clip == 3) window_kernel<3><<<grid, bs, 0, st>>>(A);
+  else window_kernel<7><<<grid, bs, 0, st>>>(A);
   return check_launch("window_kernel");
 }

@@ -50,6 +50,13 @@ def test_window_host_logic_vs_reference_golden(name):
         assert list(margin) == g["margin"][i].tolist()
         t = win.get_affine_transform(g["center"][i], g["scale"][i], 0, g["image_size"])
         assert np.abs(t - g["trans"][i]).max() < 1e-5
+    # every position of short and long videos, both numbering schemes, distances 1..3, with and without missing files
+    for is18 in (False, True):
+        for n in (1, 2, 3, 4, 7):
+            for dist in (1, 2, 3):
+                for cur in range(0 if is18 else 1, n if is18 else n + 1):
+                    for ex in (lambda i: True, lambda i: i % 3 != 1):
+                        assert win.frame_window(cur, n, is18, dist, ex) == wo.frame_window(cur, n, is18, dist, ex)
     # the two ends of a video and a one-frame video
     assert win.frame_window(0, 5, True, 2) == ((0, 1, 0, 1), (0, 1, 0, 1))
     assert win.frame_window(1, 5, False, 2) == ((1, 2, 1, 2), (0, 1, 0, 1))
