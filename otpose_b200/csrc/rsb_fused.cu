@@ -27,7 +27,6 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
-#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -552,10 +551,6 @@ bool build_level(const RsbShape &s, const std::vector<LevelOp> &ops, int b, int 
     if (best < 0 || cost <= best) best = cost, th = c;
   }
   if (th < 1) return false;
-  if (const char *e = getenv("OTP_RSB_TH")) {   // tuning probe
-    const int v = atoi(e);
-    if (v >= 1 && wbytes + (size_t)(v + 2 * a.halo) * row_bytes <= RSMEM) th = std::min(v, H);
-  }
   a.TH = th, a.tiles_y = ceil_div(H, th), a.rows = th + 2 * a.halo;
   size_t off = wbytes;
   a.tile_off = (int)off;
