@@ -184,11 +184,17 @@ __global__ void __launch_bounds__(FTH, 1) flow_encoder_kernel(const __grid_const
   // ---- residual stream: x + positional embedding (ConvVideoTransformer.py:147-157) ----
   {
     const float *xb = A.x + (size_t)b * FC * T;
-    for (int e = threadIdx.x; e < FC * nrows; e += FTH) {
-      const int c = e / nrows, r = e % nrows, tok = e0 + r;
-      float v = 0.f;
-      if (tok >= 0 && tok < T) v = __ldg(xb + (size_t)c * T + tok) + (A.pe ? __ldg(A.pe + (size_t)c * A.pe_stride + tok) : 0.f);
-      xs[r * FXS + c] = v;
+    for (int r = threadIdx.x; r < nrows; r += FTH) {   // thread = token: 34 coalesced loads in flight
+      const int tok = e0 + r;
+      const bool ok = tok >= 0 && tok < T;
+      float v[FC], pe[FC];
+#pragma unroll
+      for (int c = 0; c < FC; ++c) {
+        v[c] = ok ? __ldg(xb + (size_t)c * T + tok) : 0.f;
+        pe[c] = (ok && A.pe) ? __ldg(A.pe + (size_t)c * A.pe_stride + tok) : 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < FC; ++c) xs[r * FXS + c] = v[c] + pe[c];
     }
     for (int r = threadIdx.x; r <= nrows; r += FTH) xs[r * FXS + 17] = 0.f;
     if (threadIdx.x < FXS) xs[nrows * FXS + threadIdx.x] = 0.f;
@@ -258,52 +264,70 @@ __global__ void __launch_bounds__(FTH, 1) flow_encoder_kernel(const __grid_const
   for (int blk = 0; blk < A.nblocks; ++blk) {
     const BlockPack &P = A.blk[blk];
     __syncthreads();   // the previous block's tiles are done with the weights and with xs
-    // ---- this block's weights: fp32 vectors, augmented q / k / v projections, B-operand fragments ----
+    // ---- this block's weights: the raw fp32 sections of the pack are staged in shared memory first (one round of
+    //      coalesced loads; the staging area is the per-warp Gram scratch, dead between blocks), then the fp32
+    //      vectors, the augmented q / k / v projections and the B-operand fragments are formed from it ----
+    float *st = wpart;
+    int st_off = 0;
+    auto take = [&](const float *src, int n) {
+      const int o = st_off;
+      for (int i = threadIdx.x; i < n; i += FTH) st[o + i] = __ldg(src + i);
+      st_off += n;
+      return o;
+    };
+    const int o_wq = take(P.wqT, FC * FNP), o_wk = take(P.wkT, FC * FNP), o_wv = take(P.wv, FC * FC);
+    const int o_wp = take(P.wpT, FC * FNP), o_w1 = take(P.w1T, 4 * FC * FNP), o_w2 = take(P.w2T, 4 * FC * FNP);
+    const int o_l1w = take(P.ln1_w, FC), o_l1b = take(P.ln1_b, FC), o_l2w = take(P.ln2_w, FC), o_l2b = take(P.ln2_b, FC);
+    const int o_qnw = take(P.qn_w, FC), o_qnb = take(P.qn_b, FC), o_knw = take(P.kn_w, FC), o_knb = take(P.kn_b, FC);
+    const int o_vnw = take(P.vn_w, FC), o_vnb = take(P.vn_b, FC);
+    const int o_dq = take(P.dwq, 3 * FC), o_dk = take(P.dwk, 3 * FC), o_dv = take(P.dwv, 3 * FC);
+    const int o_bq = take(P.bq, FNP), o_bk = take(P.bk, FNP), o_bv = take(P.bv, FNP), o_bp = take(P.bp, FNP);
+    const int o_b2 = take(P.b2, FNP), o_sa = take(P.sa, FNP), o_sm = take(P.sm, FNP), o_b1 = take(P.b1, 4 * FNP);
+    __syncthreads();
     for (int e = threadIdx.x; e < 24; e += FTH) {
       const bool in = e < FC;
-      ln1g[e] = in ? __ldg(P.ln1_w + e) : 0.f;
-      ln1b[e] = in ? __ldg(P.ln1_b + e) : 0.f;
-      sa_s[e] = in ? __ldg(P.sa + e) : 0.f;
-      sm_s[e] = in ? __ldg(P.sm + e) : 0.f;
-      b2_s[e] = in ? __ldg(P.b2 + e) : 0.f;
+      ln1g[e] = in ? st[o_l1w + e] : 0.f;
+      ln1b[e] = in ? st[o_l1b + e] : 0.f;
+      sa_s[e] = in ? st[o_sa + e] : 0.f;
+      sm_s[e] = in ? st[o_sm + e] : 0.f;
+      b2_s[e] = in ? st[o_b2 + e] : 0.f;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        dws[0][k][e] = in ? __ldg(P.dwq + 3 * e + k) : 0.f;
-        dws[1][k][e] = in ? __ldg(P.dwk + 3 * e + k) : 0.f;
-        dws[2][k][e] = in ? __ldg(P.dwv + 3 * e + k) : 0.f;
+        dws[0][k][e] = in ? st[o_dq + 3 * e + k] : 0.f;
+        dws[1][k][e] = in ? st[o_dk + 3 * e + k] : 0.f;
+        dws[2][k][e] = in ? st[o_dv + 3 * e + k] : 0.f;
       }
     }
     for (int e = threadIdx.x; e < 3 * FC * FNP; e += FTH) {
       // W~[i][l] = W[i][l] g[l] (l < 17),  W~[i][17] = b[i] + sum_l W[i][l] beta[l]:  W (g * a^ + beta) + b
       const int m = e / (FC * FNP), i = (e / FNP) % FC, l = e % FNP;
-      const float *gam = m == 0 ? P.qn_w : (m == 1 ? P.kn_w : P.vn_w);
-      const float *bet = m == 0 ? P.qn_b : (m == 1 ? P.kn_b : P.vn_b);
-      const float *bias = m == 0 ? P.bq : (m == 1 ? P.bk : P.bv);
-      auto w = [&](int c) { return m == 0 ? __ldg(P.wqT + c * FNP + i) : (m == 1 ? __ldg(P.wkT + c * FNP + i) : __ldg(P.wv + i * FC + c)); };
+      const int gam = m == 0 ? o_qnw : (m == 1 ? o_knw : o_vnw), bet = m == 0 ? o_qnb : (m == 1 ? o_knb : o_vnb);
+      const int bias = m == 0 ? o_bq : (m == 1 ? o_bk : o_bv);
+      auto w = [&](int c) { return m == 0 ? st[o_wq + c * FNP + i] : (m == 1 ? st[o_wk + c * FNP + i] : st[o_wv + i * FC + c]); };
       float v;
       if (l < FC) {
-        v = w(l) * __ldg(gam + l);
+        v = w(l) * st[gam + l];
       } else {
-        v = __ldg(bias + i);
-        for (int c = 0; c < FC; ++c) v = fmaf(w(c), __ldg(bet + c), v);
+        v = st[bias + i];
+        for (int c = 0; c < FC; ++c) v = fmaf(w(c), st[bet + c], v);
       }
       (m == 0 ? wq_s : (m == 1 ? wk_s : wv_s))[i * FNP + l] = v;
     }
     build_bfrag(wp_f, wp_l, 2, 3, [&](int n, int k) {   // Wp~[n][k]: proj, bias in column 17
       if (n >= FC || k > FC) return 0.f;
-      return k < FC ? __ldg(P.wpT + k * FNP + n) : __ldg(P.bp + n);
+      return k < FC ? st[o_wp + k * FNP + n] : st[o_bp + n];
     });
     build_bfrag(w1_f, w1_l, 2, 9, [&](int n, int k) {   // W1~[n][k] = W1[n][k] g2[k]; column 17: b1[n] + sum_c W1[n][c] beta2[c]
       if (n >= FHID || k > FC) return 0.f;
-      const float *w1 = P.w1T + (size_t)(n / FC) * FC * FNP + n % FC;   // W1[n][c] = w1[c * FNP]
-      if (k < FC) return __ldg(w1 + k * FNP) * __ldg(P.ln2_w + k);
-      float v = __ldg(P.b1 + (n / FC) * FNP + n % FC);
-      for (int c = 0; c < FC; ++c) v = fmaf(__ldg(w1 + c * FNP), __ldg(P.ln2_b + c), v);
+      const float *w1 = st + o_w1 + (n / FC) * FC * FNP + n % FC;   // W1[n][c] = w1[c * FNP]
+      if (k < FC) return w1[k * FNP] * st[o_l2w + k];
+      float v = st[o_b1 + (n / FC) * FNP + n % FC];
+      for (int c = 0; c < FC; ++c) v = fmaf(w1[c * FNP], st[o_l2b + c], v);
       return v;
     });
     build_bfrag(w2_f, w2_l, 5, 3, [&](int n, int k) {   // W2[n][k], k = hidden unit
       if (n >= FC || k >= FHID) return 0.f;
-      return __ldg(P.w2T + (size_t)(k / FC) * FC * FNP + (k % FC) * FNP + n);
+      return st[o_w2 + (k / FC) * FC * FNP + (k % FC) * FNP + n];
     });
     __syncthreads();
 
