@@ -47,6 +47,7 @@ constexpr int FMAXBLK = 8;
 constexpr int FMAXPER = 1728;              // owned tokens per CTA (6912 / 4)
 constexpr int FG = 18 * 18;                // augmented Gram
 constexpr int FHID = 4 * FC;               // 68 hidden units, 9 n8 tiles
+constexpr int FSTAGE = 4224;               // floats of a block's raw weight sections (staging area)
 
 struct FlowArgs {
   BlockPack blk[FMAXBLK];
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(FTH, 1) flow_encoder_kernel(const __grid_const
   const int e0 = o0 - FHALO;                          // token of local row 0
   const int nrows = per + 2 * FHALO, ntile = nrows / 16;
   float *xs = dsm;                                    // [nrows][FXS] (+ one spare row)
-  float *wpart = dsm + (size_t)(nrows + 1) * FXS;     // [FNW][FG]
+  float *wpart = dsm + (size_t)(nrows + 1) * FXS;     // [FNW][FG], then the weight staging area [FSTAGE]
 
   // ---- residual stream: x + positional embedding (ConvVideoTransformer.py:147-157) ----
   {
@@ -261,28 +262,38 @@ __global__ void __launch_bounds__(FTH, 1) flow_encoder_kernel(const __grid_const
   };
   const int own_lo = FHALO, own_hi = FHALO + max(0, o1 - o0);   // owned local rows [own_lo, own_hi)
 
-  for (int blk = 0; blk < A.nblocks; ++blk) {
-    const BlockPack &P = A.blk[blk];
-    __syncthreads();   // the previous block's tiles are done with the weights and with xs
-    // ---- this block's weights: the raw fp32 sections of the pack are staged in shared memory first (one round of
-    //      coalesced loads; the staging area is the per-warp Gram scratch, dead between blocks), then the fp32
-    //      vectors, the augmented q / k / v projections and the B-operand fragments are formed from it ----
-    float *st = wpart;
-    int st_off = 0;
-    auto take = [&](const float *src, int n) {
-      const int o = st_off;
-      for (int i = threadIdx.x; i < n; i += FTH) st[o + i] = __ldg(src + i);
-      st_off += n;
-      return o;
+  // staging area of a block's raw fp32 weight sections (same offsets for every block), filled by 4-byte cp.async
+  float *st = wpart + FNW * FG;
+  constexpr int o_wq = 0, o_wk = o_wq + FC * FNP, o_wv = o_wk + FC * FNP, o_wp = o_wv + FC * FC, o_w1 = o_wp + FC * FNP;
+  constexpr int o_w2 = o_w1 + 4 * FC * FNP, o_l1w = o_w2 + 4 * FC * FNP, o_l1b = o_l1w + FC, o_l2w = o_l1b + FC;
+  constexpr int o_l2b = o_l2w + FC, o_qnw = o_l2b + FC, o_qnb = o_qnw + FC, o_knw = o_qnb + FC, o_knb = o_knw + FC;
+  constexpr int o_vnw = o_knb + FC, o_vnb = o_vnw + FC, o_dq = o_vnb + FC, o_dk = o_dq + 3 * FC, o_dv = o_dk + 3 * FC;
+  constexpr int o_bq = o_dv + 3 * FC, o_bk = o_bq + FNP, o_bv = o_bk + FNP, o_bp = o_bv + FNP, o_b2 = o_bp + FNP;
+  constexpr int o_sa = o_b2 + FNP, o_sm = o_sa + FNP, o_b1 = o_sm + FNP;
+  static_assert(o_b1 + 4 * FNP <= FSTAGE, "staging area");
+  auto stage_block = [&](const BlockPack &Q) {
+    auto take = [&](int o, const float *src, int n) {
+      for (int i = threadIdx.x; i < n; i += FTH)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tc::smem_u32(st + o + i)), "l"(src + i) : "memory");
     };
-    const int o_wq = take(P.wqT, FC * FNP), o_wk = take(P.wkT, FC * FNP), o_wv = take(P.wv, FC * FC);
-    const int o_wp = take(P.wpT, FC * FNP), o_w1 = take(P.w1T, 4 * FC * FNP), o_w2 = take(P.w2T, 4 * FC * FNP);
-    const int o_l1w = take(P.ln1_w, FC), o_l1b = take(P.ln1_b, FC), o_l2w = take(P.ln2_w, FC), o_l2b = take(P.ln2_b, FC);
-    const int o_qnw = take(P.qn_w, FC), o_qnb = take(P.qn_b, FC), o_knw = take(P.kn_w, FC), o_knb = take(P.kn_b, FC);
-    const int o_vnw = take(P.vn_w, FC), o_vnb = take(P.vn_b, FC);
-    const int o_dq = take(P.dwq, 3 * FC), o_dk = take(P.dwk, 3 * FC), o_dv = take(P.dwv, 3 * FC);
-    const int o_bq = take(P.bq, FNP), o_bk = take(P.bk, FNP), o_bv = take(P.bv, FNP), o_bp = take(P.bp, FNP);
-    const int o_b2 = take(P.b2, FNP), o_sa = take(P.sa, FNP), o_sm = take(P.sm, FNP), o_b1 = take(P.b1, 4 * FNP);
+    take(o_wq, Q.wqT, FC * FNP), take(o_wk, Q.wkT, FC * FNP), take(o_wv, Q.wv, FC * FC), take(o_wp, Q.wpT, FC * FNP);
+    take(o_w1, Q.w1T, 4 * FC * FNP), take(o_w2, Q.w2T, 4 * FC * FNP);
+    take(o_l1w, Q.ln1_w, FC), take(o_l1b, Q.ln1_b, FC), take(o_l2w, Q.ln2_w, FC), take(o_l2b, Q.ln2_b, FC);
+    take(o_qnw, Q.qn_w, FC), take(o_qnb, Q.qn_b, FC), take(o_knw, Q.kn_w, FC), take(o_knb, Q.kn_b, FC);
+    take(o_vnw, Q.vn_w, FC), take(o_vnb, Q.vn_b, FC);
+    take(o_dq, Q.dwq, 3 * FC), take(o_dk, Q.dwk, 3 * FC), take(o_dv, Q.dwv, 3 * FC);
+    take(o_bq, Q.bq, FNP), take(o_bk, Q.bk, FNP), take(o_bv, Q.bv, FNP), take(o_bp, Q.bp, FNP);
+    take(o_b2, Q.b2, FNP), take(o_sa, Q.sa, FNP), take(o_sm, Q.sm, FNP), take(o_b1, Q.b1, 4 * FNP);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage_block(A.blk[0]);
+
+  for (int blk = 0; blk < A.nblocks; ++blk) {
+    __syncthreads();   // the previous block's tiles are done with the weights and with xs
+    // ---- this block's weights: the raw fp32 sections of the pack were prefetched into the staging area by cp.async
+    //      (under the previous block's tile phases); the fp32 vectors, the augmented q / k / v projections and the
+    //      B-operand fragments are formed from it ----
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     for (int e = threadIdx.x; e < 24; e += FTH) {
       const bool in = e < FC;
@@ -330,6 +341,7 @@ __global__ void __launch_bounds__(FTH, 1) flow_encoder_kernel(const __grid_const
       return st[o_w2 + (k / FC) * FC * FNP + (k % FC) * FNP + n];
     });
     __syncthreads();
+    if (blk + 1 < A.nblocks) stage_block(A.blk[blk + 1]);   // lands under this block's tile phases
 
     // ================= front: G~ = sum over the owned tokens of [a;1][c;1]^T =================
     {
@@ -628,11 +640,11 @@ extern "C" int otp_flow_encoder_forward(const void *const *packed_blocks, int nb
   A.cs = flow_cluster_size(b, t);
   A.per = ceil_div(ceil_div(t, A.cs), 16) * 16;
   const int nrows = A.per + 2 * FHALO;
-  const size_t smem = ((size_t)(nrows + 1) * FXS + (size_t)FNW * FG) * sizeof(float);
+  const size_t smem = ((size_t)(nrows + 1) * FXS + (size_t)FNW * FG + FSTAGE) * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
   static PerDeviceOnce attr;
   if (attr.first()) {
-    const size_t lim = ((size_t)(FMAXPER + 2 * FHALO + 1) * FXS + (size_t)FNW * FG) * sizeof(float);
+    const size_t lim = ((size_t)(FMAXPER + 2 * FHALO + 1) * FXS + (size_t)FNW * FG + FSTAGE) * sizeof(float);
     if (!set_max_smem(flow_encoder_kernel, lim, "flow_encoder_kernel")) return OTP_ERR_CUDA;
   }
   cudaLaunchConfig_t cfg{};
