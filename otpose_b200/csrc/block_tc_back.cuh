@@ -36,7 +36,7 @@
 //    store path for ~2.5 k cycles per tile while the tensor pipe idled (and one 512-byte cp.async.bulk per
 //    channel cost the issuing warp ~80 cycles per lane).
 //
-// Optional phase trace (otp_debug_trace): CTA 0 records (clock64 << 8 | event) for epilogue warp 0
+// Optional phase trace (build with -DOTP_BACK_TRACE, then otp_debug_trace): CTA 0 records (clock64 << 8 | event) for epilogue warp 0
 // (row 0), the control warp (row 1) and epilogue warp 15 (row 2).
 constexpr int kTraceLen = 2048;
 __device__ unsigned long long g_back_trace[4][kTraceLen];   // tc_back: epilogue warp 0, control, epilogue warp 15;
@@ -234,7 +234,12 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const uint8_t *__re
     const uint32_t idesc144 = make_idesc_16(kKP, false, false, kFmt);
     const uint32_t idescP = make_idesc_16(kKP, true, false, kFmt);   // A = out2 tile, token-contiguous
     const uint32_t ab = smem_u32(abuf), rr = smem_u32(ring), hb = smem_u32(hbuf);
+#ifdef OTP_BACK_TRACE
     Tracer tr{(trace && blockIdx.x == 0 && lane == 0) ? g_back_trace[1] : nullptr, 0};
+#else
+    auto tr = [](int) {};   // compiled out by default (build with -DOTP_BACK_TRACE for scripts/trace_back.py): the 25
+                            // trace points of a tile were 4.6 % of the kernel's instructions even when switched off
+#endif
     int slot = 0;          // ring slot of the next weight piece (pieces are consumed in load order)
     uint32_t round = 0;
     // One weight image = 3 K-slices of 48 (x 2 in bfloat16 mode: hi, lo): D (+)= A[:, K] . W[:, K]^T.
@@ -298,7 +303,11 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const uint8_t *__re
     const int tok = q4 * 32 + lane;
     const int cq = quarter * kCQ;
     const bool aligned = (Tout & 7) == 0;
+#ifdef OTP_BACK_TRACE
     Tracer tr{(trace && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 15)) ? g_back_trace[warp ? 2 : 0] : nullptr, 0};
+#else
+    auto tr = [](int) {};
+#endif
     // out2 tile of tile g: channel c of the (C, T') view is the contiguous run obuf_b[c*T' + t0 ...].
     // The copy is cut into kStageParts slices so that the next tile's slices can be issued between the
     // MLP chunks, in the slack the epilogue warps have there anyway.

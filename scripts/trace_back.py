@@ -1,4 +1,4 @@
-"""Phase timeline of tc_back (CTA 0) from otp_debug_trace: per event the median cycle offset
+"""(build the library with NVCC_EXTRA=-DOTP_BACK_TRACE first)  Phase timeline of tc_back (CTA 0) from otp_debug_trace: per event the median cycle offset
 from the tile start and the median duration since the previous event of the same role.
 
     python scripts/trace_back.py [batch] [tokens]
