@@ -453,7 +453,7 @@ tc_back_kernel(BlockPack P, const uint8_t *__restrict__ tcw, const uint8_t *__re
                (float)kCQ * (d0 * d0 + d1 * d1 + d2 * d2) + kN3 * d3 * d3) * (1.0f / kC);
       }
       {
-        const float rstd = 1.0f / sqrtf(var + 1e-5f);
+        const float rstd = rsqrtf(var + 1e-5f);
         float h[kCQ];
 #pragma unroll
         for (int i = 0; i < kCQ; ++i) {

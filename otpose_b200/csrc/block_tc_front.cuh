@@ -275,7 +275,7 @@ tc_front1_kernel(BlockPack P, const float *__restrict__ x, const __grid_constant
         const float d0 = m0 - mu, d1 = m1 - mu, d2 = m2 - mu;
         const float var = (V->part[pp][3][0][tok] + V->part[pp][3][1][tok] + V->part[pp][3][2][tok] +
                            48.f * (d0 * d0 + d1 * d1) + 40.f * d2 * d2) * (1.0f / kC);
-        const float rstd = 1.0f / sqrtf(var + 1e-5f);
+        const float rstd = rsqrtf(var + 1e-5f);
         uint8_t *dst = hs + tok * kHsRow + c_lo * 2;
 #pragma unroll
         for (int g = 0; g < 6; ++g) {
@@ -298,7 +298,7 @@ tc_front1_kernel(BlockPack P, const float *__restrict__ x, const __grid_constant
         const float d0 = m0 - mu, d1 = m1 - mu, d2 = m2 - mu;
         const float var = (V->part[pp][1][0][tok] + V->part[pp][1][1][tok] + V->part[pp][1][2][tok] +
                            48.f * (d0 * d0 + d1 * d1) + 40.f * d2 * d2) * (1.0f / kC);
-        const float rstd = 1.0f / sqrtf(var + 1e-5f);
+        const float rstd = rsqrtf(var + 1e-5f);
         pp ^= 1;
         uint8_t *dst = hs + tok * kHsRow + c_lo * 2;
 #pragma unroll
@@ -391,7 +391,7 @@ tc_front1_kernel(BlockPack P, const float *__restrict__ x, const __grid_constant
         const float mean = (V->part[pp][0][0][tok] + V->part[pp][0][1][tok] + V->part[pp][0][2][tok]) * (1.0f / kC);
         const float var = fmaxf((V->part[pp][1][0][tok] + V->part[pp][1][1][tok] + V->part[pp][1][2][tok]) * (1.0f / kC) -
                                     mean * mean, 0.f);
-        const float rstd = 1.0f / sqrtf(var + 1e-5f);
+        const float rstd = rsqrtf(var + 1e-5f);
         const float nmr = -mean * rstd;   // (d - mean) * rstd as one FMA
         pp ^= 1;
         // the Gram UMMAs of the previous tile still read the a~ / c~ tiles (they were issued a whole LN1 phase
