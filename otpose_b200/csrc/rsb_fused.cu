@@ -106,39 +106,54 @@ template <int NT, int MG>
 __device__ __forceinline__ void conv_epilogue(const RsbArgs &A, const RsbOp &op, const uint8_t *sm,
                                               const float (&acc)[MG][NT][4], int b, int r, int m0) {
   const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
-  const float *bias = reinterpret_cast<const float *>(sm) + op.bofs;
-  const size_t P = (size_t)A.H * A.W;
-  __half *prow = op.plane >= 0 ? A.planes + ((((size_t)op.plane * A.B + b) * A.H + r) * A.W) * A.cp : nullptr;
+  const float *bias = reinterpret_cast<const float *>(sm) + op.bofs + 2 * q;
+  float2 bs[NT];
 #pragma unroll
-  for (int m = 0; m < MG; ++m) {
-    float res[NT][4];
-    if (op.plane < 0) {   // identity skip: every load of the tile in flight before the first store
+  for (int n = 0; n < NT; ++n) bs[n] = *reinterpret_cast<const float2 *>(bias + 8 * n);
+  if (op.plane >= 0) {
+    // ---- 16-bit plane: one base pointer per (m-tile, row half), the n-tiles are 16-byte steps from it ----
+    __half *prow = A.planes + ((((size_t)op.plane * A.B + b) * A.H + r) * A.W) * A.cp + 2 * q;
+    const bool relu = op.relu != 0;
 #pragma unroll
-      for (int n = 0; n < NT; ++n)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int p = 16 * (m0 + m) + g + 8 * (i >> 1), ch = 8 * n + 2 * q + (i & 1);
-          const bool ld = A.res && p < A.W && ch < op.gch;
-          res[n][i] = ld ? __ldg(A.res + (size_t)b * A.res_bs + (size_t)ch * P + (size_t)r * A.W + p) : 0.f;
-        }
-    }
-#pragma unroll
-    for (int n = 0; n < NT; ++n) {
-      const int ch = 8 * n + 2 * q;
-      const float2 bs = *reinterpret_cast<const float2 *>(bias + ch);
+    for (int m = 0; m < MG; ++m)
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const int p = 16 * (m0 + m) + g + 8 * hh;
         if (p >= A.W) continue;
-        float v0 = acc[m][n][2 * hh] + bs.x, v1 = acc[m][n][2 * hh + 1] + bs.y;
-        if (op.plane < 0) {
-          const size_t px = (size_t)r * A.W + p;
-          if (ch < op.gch) A.y[(size_t)b * A.y_bs + (size_t)ch * P + px] = fmaxf(v0 + res[n][2 * hh], 0.f);
-          if (ch + 1 < op.gch) A.y[(size_t)b * A.y_bs + (size_t)(ch + 1) * P + px] = fmaxf(v1 + res[n][2 * hh + 1], 0.f);
-          continue;
+        uint32_t *dst = reinterpret_cast<uint32_t *>(prow + (size_t)p * A.cp);
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+          float v0 = acc[m][n][2 * hh] + bs[n].x, v1 = acc[m][n][2 * hh + 1] + bs[n].y;
+          if (relu) v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f);
+          dst[4 * n] = pack16x2<true>(v0, v1);
         }
-        if (op.relu) v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f);
-        *reinterpret_cast<uint32_t *>(prow + (size_t)p * A.cp + ch) = pack16x2<true>(v0, v1);
+      }
+    return;
+  }
+  // ---- the block's fp32 NCHW output: + identity skip, ReLU ----
+  const size_t P = (size_t)A.H * A.W;
+  float *yb = A.y + (size_t)b * A.y_bs + (size_t)r * A.W + (size_t)(2 * q) * P;
+  const float *rb = A.res ? A.res + (size_t)b * A.res_bs + (size_t)r * A.W + (size_t)(2 * q) * P : nullptr;
+#pragma unroll
+  for (int m = 0; m < MG; ++m) {
+    float res[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n)   // every skip load of the tile in flight before the first store
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int p = 16 * (m0 + m) + g + 8 * (i >> 1), ch = 8 * n + 2 * q + (i & 1);
+        res[n][i] = (rb && p < A.W && ch < op.gch) ? __ldg(rb + (size_t)(8 * n + (i & 1)) * P + p) : 0.f;
+      }
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      const int ch = 8 * n + 2 * q;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int p = 16 * (m0 + m) + g + 8 * hh;
+        if (p >= A.W) continue;
+        float *yp = yb + (size_t)(8 * n) * P + p;
+        if (ch < op.gch) yp[0] = fmaxf(acc[m][n][2 * hh] + bs[n].x + res[n][2 * hh], 0.f);
+        if (ch + 1 < op.gch) yp[P] = fmaxf(acc[m][n][2 * hh + 1] + bs[n].y + res[n][2 * hh + 1], 0.f);
       }
     }
   }
@@ -370,9 +385,12 @@ __global__ void __launch_bounds__(RTH, 2) rsb_level_kernel(const __grid_constant
   // ---- tasks: (op, image row, group of <= RMG m-tiles), round-robin over the warps ----
   constexpr int GM = (CPB > 0 || NT1 < 3) ? RMG : 2;   // m-tiles per task (the wide 1x1 accumulators: 2)
   const int ngrp = (A.MT + GM - 1) / GM, nrow = tr1 - tr0;
+  // task -> (op, row, group) with two float-reciprocal divisions (exact for these small integers)
+  const float inv_grp = 1.0f / (float)ngrp, inv_row = 1.0f / (float)nrow;
   for (int task = warp; task < A.nop * nrow * ngrp; task += RNW) {
-    const RsbOp &op = A.op[task / (nrow * ngrp)];
-    const int jr = (task / ngrp) % nrow, m0 = (task % ngrp) * GM, mg = min(GM, A.MT - m0);
+    const int q1 = (int)(((float)task + 0.5f) * inv_grp), oi = (int)(((float)q1 + 0.5f) * inv_row);
+    const RsbOp &op = A.op[oi];
+    const int jr = q1 - oi * nrow, m0 = (task - q1 * ngrp) * GM, mg = min(GM, A.MT - m0);
     const int r = tr0 + jr, j = jr + A.halo;
     if constexpr (CPB > 0) {
       if (op.nin == 2) {
