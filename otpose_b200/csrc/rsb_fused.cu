@@ -358,12 +358,17 @@ __global__ void __launch_bounds__(RTH, 2) rsb_level_kernel(const __grid_constant
         for (int cb0 = 0; cb0 < ncb; cb0 += 4) {
           float v[4][8];
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
+          for (int u = 0; u < 4; ++u) {
+            const int c0 = 8 * (cb0 + u);
+            const float *s8 = src + (size_t)c0 * P;      // one 64-bit product per channel block, then steps of P
+            if (ok && c0 + 8 <= A.cin) {                 // a whole block of real channels: no per-channel test
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int c = 8 * (cb0 + u) + e;
-              v[u][e] = (ok && c < A.cin) ? __ldg(src + (size_t)c * P) : 0.f;
+              for (int e = 0; e < 8; ++e) v[u][e] = __ldg(s8 + (size_t)e * P);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[u][e] = (ok && c0 + e < A.cin) ? __ldg(s8 + (size_t)e * P) : 0.f;
             }
+          }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             if (cb0 + u >= ncb) continue;
