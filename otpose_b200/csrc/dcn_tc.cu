@@ -105,10 +105,12 @@ tc_dcn_fused_kernel(const uint8_t *__restrict__ wimg, const float *__restrict__ 
         const int hh = h + (t / 3 - 1) * dil, ww = w + (t % 3 - 1) * dil;
         const bool ok = live && hh >= 0 && hh < H && ww >= 0 && ww < W;
         const float *src = tb + (ok ? hh * W + ww : 0);
+        if (ok) {      // one branch per tap instead of a select per channel; channel c is c * P elements further
 #pragma unroll
-        for (int c = 0; c < kCin; ++c) {
-          v[tt][c] = ok ? __ldg(src) : 0.f;
-          src += P;
+          for (int c = 0; c < kCin; ++c) v[tt][c] = __ldg(src + (size_t)c * P);
+        } else {
+#pragma unroll
+          for (int c = 0; c < kCin; ++c) v[tt][c] = 0.f;
         }
       }
 #pragma unroll
